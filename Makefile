@@ -1,0 +1,70 @@
+# Build of libgiddy_b200 (product), the test oracle, and -- when /root/reference is present --
+# the reference rebuilt for sm_100a (oracle/_ref, test infrastructure only).
+#
+#   make            product library + oracle
+#   make ref        the reference oracle (needs /root/reference; see oracle/build_ref.sh)
+#   make examples   C++ examples (link against the product library)
+#   make sass       SASS / resource-usage listings into profiles/
+#
+# All device code is compiled for sm_100a only.
+
+CUDA_HOME ?= /usr/local/cuda
+NVCC      ?= $(CUDA_HOME)/bin/nvcc
+# the environment's CXX may point at a wrapper without OpenMP support; use the system compiler
+CXX       := /usr/bin/g++
+
+ARCH_FLAGS := -gencode arch=compute_100a,code=sm_100a
+NVCC_FLAGS := -std=c++17 -O3 -lineinfo $(ARCH_FLAGS) -Xcompiler -fPIC,-fvisibility=hidden -Iinclude -Iinclude/giddy --expt-relaxed-constexpr -diag-suppress 186,1160
+CXX_FLAGS  := -std=c++17 -O2 -fPIC -fvisibility=hidden -Wall -Wextra -Wno-unused-parameter -Iinclude -Iinclude/giddy -I$(CUDA_HOME)/include
+
+SRC_DIR   := libgiddy_b200/csrc
+BUILD_DIR := build
+LIB_DIR   := libgiddy_b200/lib
+LIB       := $(LIB_DIR)/libgiddy_b200.so
+
+ABI_SRCS  := $(wildcard $(SRC_DIR)/abi/*.cu)
+HOST_SRCS := $(wildcard $(SRC_DIR)/host/*.cpp)
+ABI_OBJS  := $(patsubst $(SRC_DIR)/abi/%.cu,$(BUILD_DIR)/abi/%.o,$(ABI_SRCS))
+HOST_OBJS := $(patsubst $(SRC_DIR)/host/%.cpp,$(BUILD_DIR)/host/%.o,$(HOST_SRCS))
+KERNEL_HDRS := $(wildcard $(SRC_DIR)/kernels/*.cuh) $(wildcard $(SRC_DIR)/abi/*.hpp) include/giddy_b200.h
+HOST_HDRS := $(wildcard include/giddy/*.hpp) $(wildcard include/giddy/*/*.hpp) $(wildcard include/giddy/*/*.h) include/giddy_b200.h
+
+ORACLE_LIB := oracle/libgiddy_oracle.so
+
+.PHONY: all lib oracle ref examples sass clean
+
+all: lib oracle
+
+lib: $(LIB)
+
+$(BUILD_DIR)/abi/%.o: $(SRC_DIR)/abi/%.cu $(KERNEL_HDRS)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(NVCC_FLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD_DIR)/abi/$*.ptxas.log || (cat $(BUILD_DIR)/abi/$*.ptxas.log; exit 1)
+
+$(BUILD_DIR)/host/%.o: $(SRC_DIR)/host/%.cpp $(HOST_HDRS)
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXX_FLAGS) -c $< -o $@
+
+$(LIB): $(ABI_OBJS) $(HOST_OBJS)
+	@mkdir -p $(LIB_DIR)
+	$(NVCC) $(ARCH_FLAGS) -shared -o $@ $^ -cudart static
+
+oracle: $(ORACLE_LIB)
+
+$(ORACLE_LIB): oracle/giddy_oracle.cpp
+	$(CXX) -std=c++17 -O3 -march=native -fopenmp -fPIC -shared -Wall -o $@ $<
+
+ref:
+	bash oracle/build_ref.sh
+
+examples: lib
+	$(MAKE) -C examples
+
+sass: lib
+	@mkdir -p profiles/sass
+	for o in $(ABI_OBJS); do b=$$(basename $$o .o); \
+		$(CUDA_HOME)/bin/cuobjdump -sass $$o > profiles/sass/$$b.sass; \
+		cp $(BUILD_DIR)/abi/$$b.ptxas.log profiles/sass/$$b.ptxas.txt; done
+
+clean:
+	rm -rf $(BUILD_DIR) $(LIB) $(ORACLE_LIB)

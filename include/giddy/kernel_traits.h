@@ -1,0 +1,30 @@
+/*
+ * giddy/kernel_traits.h -- the few compile-time constants of the device kernels which the host-side
+ * launch-configuration policy must agree with.  Included by both sides (C, C++ and CUDA compatible).
+ */
+#ifndef GIDDY_KERNEL_TRAITS_H_
+#define GIDDY_KERNEL_TRAITS_H_
+
+/* Position-aligned decoders (FOR, Model, DZB-fixed, Dictionary): a thread produces this many
+ * 16-byte output vectors per tile; a CTA owns blockDim.x * this many vectors per grid-stride step. */
+#define GIDDY_ELEMENTWISE_UNROLL 4
+#define GIDDY_ELEMENTWISE_BLOCK_THREADS 256
+
+/* Run-based decoders (RLE, RPE): a warp decodes a segment in tiles of this many positions ... */
+#define GIDDY_RUNS_TILE_POSITIONS 1024
+/* ... staging at most this many runs per tile ... */
+#define GIDDY_RUNS_STAGED_CAPACITY (GIDDY_RUNS_TILE_POSITIONS + 32)
+/* ... in this much dynamic shared memory per warp, for elements of U bytes. */
+#define GIDDY_RUNS_SHARED_BYTES_PER_WARP(U) (2 * (GIDDY_RUNS_TILE_POSITIONS / 32) * 4 + GIDDY_RUNS_STAGED_CAPACITY * (U))
+#define GIDDY_RUNS_WARPS_PER_BLOCK 4
+
+/* Warp-per-segment decoders (Delta, DZB-variable) and warp-per-tile decoders (incidence bitmaps) */
+#define GIDDY_SEGMENT_WARPS_PER_BLOCK 8
+#define GIDDY_BITMAPS_CONTAINERS_PER_TILE 32
+
+/* Patching kernels */
+#define GIDDY_SCATTER_UNROLL 8
+#define GIDDY_SCATTER_BLOCK_THREADS 256
+#define GIDDY_CI_SCATTER_WARPS_PER_BLOCK 4
+
+#endif /* GIDDY_KERNEL_TRAITS_H_ */

@@ -1,0 +1,336 @@
+/*
+ * giddy_b200.h -- the C ABI of libgiddy_b200.so
+ *
+ * A Blackwell-native (sm_100a) implementation of the decompression path of
+ * eyalroz/libgiddy.  Everything exported by the shared library is declared in
+ * this header, `extern "C"`, with plain pointers and sizes only.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) The *registry* API ("mode iii" of the reference, README.md:116-126):
+ *      string-keyed factory -> type-erased kernel wrapper -> resolve a launch
+ *      configuration from named scalar arguments -> enqueue a launch with named,
+ *      exactly-typed arguments.  This is what a foreign-language binding
+ *      (ctypes / cgo / JNI / N-API) of the reference would bind; it replaces
+ *        cuda::registered::kernel_t::produceSubclass   src/util/FactoryProducible.h:63-70
+ *        cuda::kernel_t::resolve_launch_configuration  src/cuda/kernel_wrapper.cuh:94-123
+ *        cuda::kernel_t::enqueue_launch                src/cuda/kernel_wrapper.cuh:68-71
+ *        cuda::kernel_t::get_device_function           src/cuda/kernel_wrapper.cuh:125
+ *
+ *  (2) The *kernel* API: one launcher per scheme taking the reference kernel's
+ *      parameters in the reference kernel's order, preceded by the stream, the
+ *      launch configuration and the template parameters as run-time byte sizes.
+ *      The C++ wrapper classes (include/giddy/) call only these.  Each launcher
+ *      cites the reference __global__ function it replaces.
+ *
+ * Conventions: every function returns a giddy_status_t (0 = success) unless it
+ * returns a pointer/count; on failure giddy_last_error() holds a message for the
+ * calling thread.  Launches are asynchronous on the given stream and -- like the
+ * reference (external/cuda-api-wrappers/src/cuda/api/kernel_launch.cuh:107-112) --
+ * execution errors surface at the caller's next synchronisation; launch
+ * *configuration* errors are reported immediately.  The library owns no device
+ * memory, makes no copies and never synchronises.  There is no CPU fallback.
+ */
+#ifndef GIDDY_B200_H_
+#define GIDDY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define GIDDY_API
+#else
+#define GIDDY_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Status codes: one per exception type the reference's C++ API throws        */
+/* (SURVEY.md 8b "Errors").                                                    */
+/* ------------------------------------------------------------------------- */
+typedef enum giddy_status_t {
+	GIDDY_SUCCESS            = 0,
+	GIDDY_INVALID_ARGUMENT   = 1, /* std::invalid_argument: unknown factory key, bad scheme parameter, impossible configuration */
+	GIDDY_OUT_OF_RANGE       = 2, /* std::out_of_range: a required named argument is missing (unordered_map::at) */
+	GIDDY_BAD_ANY_CAST       = 3, /* boost::bad_any_cast: a named argument does not have exactly the expected type */
+	GIDDY_LOGIC_ERROR        = 4, /* std::logic_error: e.g. a serialization factor for a kernel which admits none */
+	GIDDY_CUDA_ERROR         = 5, /* cuda::runtime_error: a CUDA runtime API call failed */
+	GIDDY_UNSUPPORTED        = 6, /* the kernel API was asked for a size combination which is not instantiated */
+	GIDDY_INTERNAL_ERROR     = 7
+} giddy_status_t;
+
+GIDDY_API const char* giddy_last_error(void);
+GIDDY_API const char* giddy_version(void);
+
+/* ------------------------------------------------------------------------- */
+/* Plain-data mirrors of the types in the reference's signatures              */
+/* ------------------------------------------------------------------------- */
+
+/* cuda::launch_configuration_t, external/cuda-api-wrappers/src/cuda/api/types.h:99-103.
+ * Only linear grids are ever produced (src/cuda/linear_grid.h).  The dynamic shared
+ * memory size is widened from the reference's unsigned short (types.h:93) to 32 bits:
+ * B200 allows 227 KiB per block. */
+typedef struct giddy_launch_config_t {
+	unsigned grid_dimensions[3];
+	unsigned block_dimensions[3];
+	unsigned dynamic_shared_memory_size;
+} giddy_launch_config_t;
+
+/* cuda::launch_configuration_limits_t, src/cuda/kernel_wrapper.cuh:20-33.
+ * A zero "has_" flag means boost::none. */
+typedef struct giddy_launch_config_limits_t {
+	int      has_block_size;             unsigned block_size;
+	int      has_grid_size;              unsigned grid_size;
+	int      has_dynamic_shared_memory;  unsigned dynamic_shared_memory;
+} giddy_launch_config_limits_t;
+
+/* The subset of cuda::device::properties_t (cudaDeviceProp) the resolver reads. */
+typedef struct giddy_device_properties_t {
+	int    compute_capability_major;
+	int    compute_capability_minor;
+	int    multiprocessor_count;
+	int    max_threads_per_block;
+	int    max_threads_dim_x;
+	int    max_threads_per_multiprocessor;
+	int    max_blocks_per_multiprocessor;
+	int    warp_size;
+	size_t shared_memory_per_block;
+	size_t shared_memory_per_block_optin;
+	size_t shared_memory_per_multiprocessor;
+	size_t l2_cache_size;
+	size_t total_global_memory;
+} giddy_device_properties_t;
+
+/* The subset of cuda::device_function::attributes_t (cudaFuncAttributes). */
+typedef struct giddy_function_attributes_t {
+	int    max_threads_per_block;
+	int    num_regs;
+	size_t shared_size_bytes;               /* static shared memory */
+	size_t const_size_bytes;
+	size_t local_size_bytes;
+	int    max_dynamic_shared_size_bytes;
+	int    ptx_version;
+	int    binary_version;
+} giddy_function_attributes_t;
+
+/* Properties of a device / of the current device (device_id < 0). */
+GIDDY_API giddy_status_t giddy_device_properties(int device_id, giddy_device_properties_t* out);
+
+/* Attributes of a kernel returned by one of the *_kernel() getters below;
+ * replaces cuda::device_function_t::attributes(), external/.../device_function.hpp:73-79.
+ * The kernels are registered with this library's CUDA runtime, so callers must ask here. */
+GIDDY_API giddy_status_t giddy_function_attributes(const void* kernel, giddy_function_attributes_t* out);
+
+/* Launch a kernel returned by one of the *_kernel() getters with a caller-built argument
+ * pack ("mode ii", src/cuda/kernel_wrapper.cuh:135-147).  `args` is cudaLaunchKernel's. */
+GIDDY_API giddy_status_t giddy_launch_kernel(const void* kernel, void* stream,
+	const giddy_launch_config_t* config, void** args);
+
+/* ------------------------------------------------------------------------- */
+/* (1) Registry API                                                           */
+/* ------------------------------------------------------------------------- */
+
+/* Exact static type of a named argument.  boost::any_cast demands the exact type
+ * (src/cuda/kernel_wrapper.cuh:47-49), and so does this API: passing GIDDY_T_U32
+ * where the wrapper expects size_t fails with GIDDY_BAD_ANY_CAST.
+ * size_t is GIDDY_T_U64; unsigned is GIDDY_T_U32; unsigned short is GIDDY_T_U16;
+ * unsigned char is GIDDY_T_U8. */
+typedef enum giddy_type_t {
+	GIDDY_T_U8 = 1, GIDDY_T_U16, GIDDY_T_U32, GIDDY_T_U64,
+	GIDDY_T_I8,     GIDDY_T_I16, GIDDY_T_I32, GIDDY_T_I64,
+	GIDDY_T_BOOL,
+	/* cuda::array<T, N> by value (model coefficients, src/cuda/stl_array.cuh:15-18) */
+	GIDDY_T_ARRAY_I16_1, GIDDY_T_ARRAY_I16_2, GIDDY_T_ARRAY_I32_1, GIDDY_T_ARRAY_I32_2,
+	/* pointers: T* = GIDDY_T_PTR | element type; const T* additionally | GIDDY_T_CONST */
+	GIDDY_T_PTR   = 0x100,
+	GIDDY_T_CONST = 0x200
+} giddy_type_t;
+
+typedef struct giddy_arg_t {
+	const char* name;
+	int         type;      /* a giddy_type_t, possibly or-ed with GIDDY_T_PTR [| GIDDY_T_CONST] */
+	union {
+		uint64_t    u;     /* unsigned scalars and bool */
+		int64_t     i;     /* signed scalars */
+		const void* p;     /* pointers (device memory) */
+		int32_t     a[2];  /* cuda::array<int16|int32, 1|2> by value */
+	} value;
+} giddy_arg_t;
+
+typedef struct giddy_kernel giddy_kernel_t;
+
+/* The factory's key set (163 keys), in sorted order.
+ * Replaces getSubclassFactory().getInsantiators(), src/util/Factory.h:98-100. */
+GIDDY_API size_t      giddy_num_registered_kernels(void);
+GIDDY_API const char* giddy_registered_kernel_key(size_t index);
+GIDDY_API int         giddy_can_produce(const char* key);
+
+/* produceSubclass(key).  Unknown key -> GIDDY_INVALID_ARGUMENT, *out = NULL. */
+GIDDY_API giddy_status_t giddy_produce_subclass(const char* key, giddy_kernel_t** out);
+GIDDY_API void           giddy_kernel_destroy(giddy_kernel_t* kernel);
+GIDDY_API const char*    giddy_kernel_key(const giddy_kernel_t* kernel);
+
+/* get_device_function(): the address of the __global__ instantiation. */
+GIDDY_API const void*    giddy_kernel_get_device_function(const giddy_kernel_t* kernel);
+
+/* resolve_launch_configuration(device_properties, kernel_function_attributes, extra_arguments, limits).
+ * device_properties == NULL: use the current device's.  attributes == NULL: query them
+ * (the 3-argument overload, src/cuda/kernel_wrapper.cuh:94-102).  limits == NULL: none. */
+GIDDY_API giddy_status_t giddy_kernel_resolve_launch_configuration(
+	const giddy_kernel_t*               kernel,
+	const giddy_device_properties_t*    device_properties,
+	const giddy_function_attributes_t*  kernel_function_attributes,
+	const giddy_arg_t*                  extra_arguments,
+	size_t                              num_extra_arguments,
+	const giddy_launch_config_limits_t* limits,
+	giddy_launch_config_t*              out);
+
+/* enqueue_launch(stream, launch_config, arguments).  The stream is assumed to belong to
+ * the current device (src/kernel_wrappers/registered_wrapper.h:82). */
+GIDDY_API giddy_status_t giddy_kernel_enqueue_launch(
+	const giddy_kernel_t*         kernel,
+	void*                         stream,
+	const giddy_launch_config_t*  launch_config,
+	const giddy_arg_t*            arguments,
+	size_t                        num_arguments);
+
+/* ------------------------------------------------------------------------- */
+/* (2) Kernel API.  Sizes are template parameters of the reference, in bytes.  */
+/* Lengths are passed as 64-bit values and narrowed to size_type_by_index_size */
+/* <IndexSize> (src/kernels/common.cuh:49-53) inside.                          */
+/* ------------------------------------------------------------------------- */
+
+typedef enum giddy_model_t { GIDDY_MODEL_CONSTANT = 0, GIDDY_MODEL_LINEAR = 1 } giddy_model_t;
+
+/* decompression::frame_of_reference::decompress<IndexSize, Uncompressed, Compressed, UnaryModelFunction>
+ * src/kernels/decompression/frame_of_reference.cuh:35-80.  Coefficients are int32 (constant: 1, linear: 2
+ * per segment).  The reference's derived parameter num_segments_to_decompress_per_block is not needed. */
+GIDDY_API const void* giddy_b200_frame_of_reference_kernel(
+	unsigned index_size, unsigned uncompressed_size, unsigned compressed_size,
+	giddy_model_t model, unsigned model_index_size);
+GIDDY_API giddy_status_t giddy_b200_frame_of_reference_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned index_size, unsigned uncompressed_size, unsigned compressed_size,
+	giddy_model_t model, unsigned model_index_size,
+	void* decompressed, const void* compressed_input, const void* segment_model_coefficients,
+	uint64_t length, uint64_t segment_length);
+
+/* decompression::model::decompress<IndexSize, Uncompressed, UnaryModelFunction>
+ * src/kernels/decompression/model.cuh:38-53.  Coefficient type == Uncompressed; passed by value. */
+GIDDY_API const void* giddy_b200_model_kernel(
+	unsigned index_size, unsigned uncompressed_size, giddy_model_t model);
+GIDDY_API giddy_status_t giddy_b200_model_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned index_size, unsigned uncompressed_size, giddy_model_t model,
+	void* decompressed, const void* model_coefficients /* host pointer to 1 or 2 coefficients */,
+	uint64_t length);
+
+/* decompression::run_length_encoding::decompress<UncompressedIndexSize, UncompressedSize, RunLengthSize, RunIndexSize>
+ * src/kernels/decompression/run_length_encoding.cuh:342-374 */
+GIDDY_API const void* giddy_b200_run_length_encoding_kernel(
+	unsigned uncompressed_index_size, unsigned uncompressed_size, unsigned run_length_size, unsigned run_index_size);
+GIDDY_API giddy_status_t giddy_b200_run_length_encoding_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned uncompressed_index_size, unsigned uncompressed_size, unsigned run_length_size, unsigned run_index_size,
+	void* decompressed, const void* run_data, const void* run_lengths,
+	const void* segment_position_anchors, const void* segment_position_anchor_intra_run_offsets,
+	uint64_t segment_length, uint64_t num_segments, uint64_t num_element_runs, uint64_t total_uncompressed_length);
+
+/* decompression::run_position_encoding::decompress<UncompressedIndexSize, UncompressedSize, PositionOffsetSize, PositionsAreRelative, RunIndexSize>
+ * src/kernels/decompression/run_position_encoding.cuh:327-359 */
+GIDDY_API const void* giddy_b200_run_position_encoding_kernel(
+	unsigned uncompressed_index_size, unsigned uncompressed_size, unsigned position_offset_size,
+	int positions_are_relative, unsigned run_index_size);
+GIDDY_API giddy_status_t giddy_b200_run_position_encoding_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned uncompressed_index_size, unsigned uncompressed_size, unsigned position_offset_size,
+	int positions_are_relative, unsigned run_index_size,
+	void* decompressed, const void* run_data, const void* run_start_positions, const void* position_anchors,
+	uint64_t anchoring_period, uint64_t num_anchors, uint64_t num_element_runs, uint64_t uncompressed_length);
+
+/* decompression::delta::decompress<IndexSize, UncompressedSize, CompressedSize>
+ * src/kernels/decompression/delta.cuh:66-108 */
+GIDDY_API const void* giddy_b200_delta_kernel(
+	unsigned index_size, unsigned uncompressed_size, unsigned compressed_size);
+GIDDY_API giddy_status_t giddy_b200_delta_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned index_size, unsigned uncompressed_size, unsigned compressed_size,
+	void* decompressed, const void* compressed_input, const void* anchor_values,
+	uint64_t length, uint64_t segment_length);
+
+/* decompression::dictionary::decompress<IndexSize, UncompressedSize, DictionaryIndexSize>
+ * src/kernels/decompression/dictionary.cuh:61-75.  cache_dictionary_in_shared_memory is honoured
+ * (the reference's shared-memory path is dead code, gather.cuh:33-90); serialization_factor is
+ * accepted and ignored, as in the reference (gather.cuh:24). */
+GIDDY_API const void* giddy_b200_dictionary_kernel(
+	unsigned index_size, unsigned uncompressed_size, unsigned dictionary_index_size);
+GIDDY_API giddy_status_t giddy_b200_dictionary_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned index_size, unsigned uncompressed_size, unsigned dictionary_index_size,
+	void* decompressed, const void* compressed_input, const void* dictionary_entries,
+	uint64_t length, uint64_t num_dictionary_entries,
+	int cache_dictionary_in_shared_memory, unsigned serialization_factor);
+
+/* decompression::discard_zero_bytes::fixed_width::decompress<IndexSize, UncompressedSize, CompressedSize, little, 32>
+ * src/kernels/decompression/discard_zero_bytes_fixed.cuh:108-124 */
+GIDDY_API const void* giddy_b200_discard_zero_bytes_fixed_kernel(
+	unsigned index_size, unsigned uncompressed_size, unsigned compressed_size);
+GIDDY_API giddy_status_t giddy_b200_discard_zero_bytes_fixed_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned index_size, unsigned uncompressed_size, unsigned compressed_size,
+	void* decompressed, const void* compressed_input, uint64_t length);
+
+/* decompression::discard_zero_bytes::variable_width::decompress<IndexSize, UncompressedSize, ElementSizesContainerSize>
+ * src/kernels/decompression/discard_zero_bytes_variable.cuh:381-439 */
+GIDDY_API const void* giddy_b200_discard_zero_bytes_variable_kernel(
+	unsigned index_size, unsigned uncompressed_size, unsigned element_sizes_container_size);
+GIDDY_API giddy_status_t giddy_b200_discard_zero_bytes_variable_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned index_size, unsigned uncompressed_size, unsigned element_sizes_container_size,
+	void* decompressed, const void* compressed_data, const void* packed_element_sizes,
+	const void* position_anchors, uint64_t segment_length, uint64_t length,
+	unsigned min_represented_element_size, unsigned bits_per_element_size);
+
+/* decompression::incidence_bitmaps::decompress<IndexSize, UncompressedSize, BitmapAlignmentInInts, UseDictionary>
+ * src/kernels/decompression/incidence_bitmaps.cuh:69-131 */
+GIDDY_API const void* giddy_b200_incidence_bitmaps_kernel(
+	unsigned index_size, unsigned uncompressed_size, unsigned bitmap_alignment_in_ints, int use_dictionary);
+GIDDY_API giddy_status_t giddy_b200_incidence_bitmaps_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned index_size, unsigned uncompressed_size, unsigned bitmap_alignment_in_ints, int use_dictionary,
+	void* decompressed, const void* bitmaps, const void* dictionary_entries,
+	uint64_t bitmap_length, unsigned num_bitmaps);
+
+/* scatter::scatter<OutputIndexSize, ElementSize, InputIndexSize, 16>
+ * src/kernels/data_layout/scatter.cuh:26-46 */
+GIDDY_API const void* giddy_b200_scatter_kernel(
+	unsigned output_index_size, unsigned element_size, unsigned input_index_size);
+GIDDY_API giddy_status_t giddy_b200_scatter_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned output_index_size, unsigned element_size, unsigned input_index_size,
+	void* target, const void* data, const void* indices, uint64_t data_length);
+
+/* scatter::compressed_indices::scatter<OutputIndexSize, ElementSize, InputIndexSize, RunLengthSize>
+ * src/kernels/data_layout/compressed_indices_scatter.cuh:219-271 */
+GIDDY_API const void* giddy_b200_compressed_indices_scatter_kernel(
+	unsigned output_index_size, unsigned element_size, unsigned input_index_size, unsigned run_length_size);
+GIDDY_API giddy_status_t giddy_b200_compressed_indices_scatter_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned output_index_size, unsigned element_size, unsigned input_index_size, unsigned run_length_size,
+	void* target, const void* data,
+	const void* scatter_position_run_lengths,
+	const void* scatter_position_run_individual_offset_sizes,
+	const void* scatter_position_run_baseline_values,
+	const void* scatter_position_run_offsets_start_positions,
+	const void* scatter_position_offset_bytes,
+	const void* scatter_position_anchors,
+	uint64_t anchoring_period, uint64_t num_scatter_position_runs, uint64_t data_length);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* GIDDY_B200_H_ */

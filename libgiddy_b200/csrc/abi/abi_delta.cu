@@ -1,0 +1,50 @@
+// C ABI launcher for the Delta decoder (include/giddy_b200.h, kernel API).
+// Instantiations: src/kernel_wrappers/decompression/delta.cu:94-106.
+#include "abi_internal.hpp"
+#include "../kernels/delta.cuh"
+
+using namespace giddy;
+using namespace giddy::abi;
+
+namespace {
+
+using delta_launcher_t = giddy_status_t (*)(void*, const giddy_launch_config_t*, void*, const void*, const void*, uint64_t, uint64_t);
+struct delta_entry_t { unsigned I, U, C; const void* kernel; delta_launcher_t launch; };
+
+template <unsigned I, unsigned U, unsigned C>
+giddy_status_t delta_launch(void* stream, const giddy_launch_config_t* cfg, void* out, const void* in, const void* anchors, uint64_t n, uint64_t L)
+{
+	return launch(kernels::delta_decompress<I, U, C>, stream, cfg,
+		static_cast<uint_t<U>*>(out), static_cast<const uint_t<C>*>(in), static_cast<const uint_t<U>*>(anchors),
+		(size_type<I>) n, (size_type<I>) L);
+}
+#define DELTA_ENTRY(I, U, C) { I, U, C, reinterpret_cast<const void*>(&kernels::delta_decompress<I, U, C>), &delta_launch<I, U, C> }
+#define DELTA_ENTRIES(I) DELTA_ENTRY(I, 2, 1), DELTA_ENTRY(I, 4, 1), DELTA_ENTRY(I, 4, 2), DELTA_ENTRY(I, 8, 1), DELTA_ENTRY(I, 8, 2), DELTA_ENTRY(I, 8, 4)
+
+const delta_entry_t delta_table[] = { DELTA_ENTRIES(4), DELTA_ENTRIES(8) };
+
+const delta_entry_t* find_delta(unsigned I, unsigned U, unsigned C)
+{
+	for (const auto& e : delta_table) { if (e.I == I && e.U == U && e.C == C) { return &e; } }
+	return nullptr;
+}
+
+} // namespace
+
+extern "C" const void* giddy_b200_delta_kernel(unsigned I, unsigned U, unsigned C)
+{
+	auto e = find_delta(I, U, C);
+	return e ? e->kernel : nullptr;
+}
+
+extern "C" giddy_status_t giddy_b200_delta_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned I, unsigned U, unsigned C,
+	void* decompressed, const void* compressed_input, const void* anchor_values, uint64_t length, uint64_t segment_length)
+{
+	auto e = find_delta(I, U, C);
+	giddy_status_t status;
+	if (!check_launch(config, e ? e->kernel : nullptr, status)) { return status; }
+	if (segment_length == 0) { return fail(GIDDY_INVALID_ARGUMENT, "The segment length must be a positive number"); }
+	if (length == 0) { return GIDDY_SUCCESS; }
+	return e->launch(stream, config, decompressed, compressed_input, anchor_values, length, segment_length);
+}

@@ -1,0 +1,52 @@
+// Internal helpers shared by the translation units which implement the C ABI (include/giddy_b200.h).
+#pragma once
+#ifndef GIDDY_B200_ABI_INTERNAL_HPP_
+#define GIDDY_B200_ABI_INTERNAL_HPP_
+
+#include "giddy_b200.h"
+#include <cuda_runtime.h>
+#include <atomic>
+#include <string>
+
+namespace giddy {
+namespace abi {
+
+// Record a message for giddy_last_error() (thread-local) and return the status.
+giddy_status_t fail(giddy_status_t status, const std::string& message);
+giddy_status_t fail_cuda(cudaError_t error, const char* what);
+
+inline dim3 to_dim3(const unsigned (&d)[3]) { return dim3(d[0], d[1] ? d[1] : 1, d[2] ? d[2] : 1); }
+
+// Kernels which want more than the default 48 KiB of dynamic shared memory must opt in once per
+// function (and per device; the attribute is sticky, so re-applying is harmless).
+inline cudaError_t ensure_dynamic_shared_memory(const void* kernel, unsigned bytes)
+{
+	if (bytes <= 48 * 1024) { return cudaSuccess; }
+	return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+}
+
+// Common prologue of every launcher.  Returns true when there is something to launch.
+inline bool check_launch(const giddy_launch_config_t* config, const void* kernel, giddy_status_t& status)
+{
+	if (config == nullptr) { status = fail(GIDDY_INVALID_ARGUMENT, "null launch configuration"); return false; }
+	if (kernel == nullptr) { status = fail(GIDDY_UNSUPPORTED, "this combination of type sizes is not instantiated"); return false; }
+	status = GIDDY_SUCCESS;
+	return true;
+}
+
+template <typename Kernel, typename... Args>
+inline giddy_status_t launch(Kernel kernel, void* stream, const giddy_launch_config_t* config, Args... args)
+{
+	cudaError_t error = ensure_dynamic_shared_memory(reinterpret_cast<const void*>(kernel), config->dynamic_shared_memory_size);
+	if (error != cudaSuccess) { return fail_cuda(error, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); }
+	kernel<<<to_dim3(config->grid_dimensions), to_dim3(config->block_dimensions),
+		config->dynamic_shared_memory_size, static_cast<cudaStream_t>(stream)>>>(args...);
+	error = cudaGetLastError();
+	if (error != cudaSuccess) { return fail_cuda(error, "kernel launch"); }
+	return GIDDY_SUCCESS;
+}
+
+} // namespace abi
+} // namespace giddy
+
+#endif // GIDDY_B200_ABI_INTERNAL_HPP_

@@ -1,0 +1,212 @@
+// Device-side building blocks shared by all giddy_b200 kernels (sm_100a).
+//
+// Everything here is integer-only.  The recurring ideas:
+//   * every global access a thread makes is as wide as alignment allows (up to
+//     128 bits) and warp-contiguous, so each warp instruction touches whole
+//     32-byte sectors;
+//   * decoded output is never re-read by these kernels, so it is written with
+//     streaming (evict-first) stores; compressed input is read through the
+//     non-coherent path without L1 allocation unless it is going to be re-read;
+//   * work is distributed at warp granularity with grid-stride loops, so every
+//     kernel is correct for any grid size and any block size that is a multiple
+//     of 32 -- the launch configuration resolver only affects speed.
+#pragma once
+#ifndef GIDDY_B200_KERNELS_COMMON_CUH_
+#define GIDDY_B200_KERNELS_COMMON_CUH_
+
+#include <cstdint>
+#include <cstddef>
+#include <type_traits>
+#include <cuda_runtime.h>
+#include "giddy/kernel_traits.h"
+
+namespace giddy {
+
+template <unsigned N> struct uint_of;
+template <> struct uint_of<1> { using type = uint8_t;  };
+template <> struct uint_of<2> { using type = uint16_t; };
+template <> struct uint_of<4> { using type = uint32_t; };
+template <> struct uint_of<8> { using type = uint64_t; };
+template <unsigned N> using uint_t = typename uint_of<N>::type;
+
+template <unsigned N> struct int_of;
+template <> struct int_of<1> { using type = int8_t;  };
+template <> struct int_of<2> { using type = int16_t; };
+template <> struct int_of<4> { using type = int32_t; };
+template <> struct int_of<8> { using type = int64_t; };
+template <unsigned N> using int_t = typename int_of<N>::type;
+
+// size_type_by_index_size<N> of the reference (src/kernels/common.cuh:49-53):
+// 32 bits for index sizes up to 4, 64 bits for 8.
+template <unsigned IndexSize>
+using size_type = typename std::conditional<(IndexSize > 4), uint64_t, uint32_t>::type;
+
+// POD array passed by value / stored per segment: the layout of the reference's
+// cuda::array<T, N> (src/cuda/stl_array.cuh:15-18,63).
+template <typename T, unsigned N> struct pod_array { T v[N]; };
+
+enum : int { model_constant = 0, model_linear = 1 };
+
+namespace device {
+
+constexpr unsigned warp_size = 32;
+constexpr unsigned full_mask = 0xffffffffu;
+
+__device__ __forceinline__ unsigned lane_index() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned warp_index_in_block() { return threadIdx.x >> 5; }
+__device__ __forceinline__ unsigned warps_per_block() { return blockDim.x >> 5; }
+__device__ __forceinline__ uint64_t global_warp_index() { return (uint64_t) blockIdx.x * warps_per_block() + warp_index_in_block(); }
+__device__ __forceinline__ uint64_t num_warps_in_grid() { return (uint64_t) gridDim.x * warps_per_block(); }
+
+// bytes must be a power of 2
+__device__ __forceinline__ bool is_aligned_to(const void* p, unsigned bytes)
+{
+	return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(bytes - 1)) == 0;
+}
+
+// ---- 128-bit streaming accessors -------------------------------------------------------------
+
+__device__ __forceinline__ uint4 load_streaming_16(const void* p)
+{
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+		: "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ uint2 load_streaming_8(const void* p)
+{
+	uint2 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ uint32_t load_streaming_4(const void* p)
+{
+	uint32_t r;
+	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ uint16_t load_streaming_2(const void* p)
+{
+	uint16_t r;
+	asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ uint8_t load_streaming_1(const void* p)
+{
+	uint32_t r;
+	asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(r) : "l"(p));
+	return (uint8_t) r;
+}
+
+__device__ __forceinline__ void store_streaming_16(void* p, const uint4& v)
+{
+	asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// A register-resident group of Bytes bytes, loadable in one (or a few) maximal-width
+// streaming accesses and addressable as elements of any power-of-2 size.
+template <unsigned Bytes>
+struct alignas(Bytes >= 16 ? 16 : Bytes) byte_pack {
+	static_assert(Bytes == 1 || Bytes == 2 || Bytes == 4 || Bytes == 8 || Bytes % 16 == 0, "unsupported pack size");
+	union {
+		uint8_t  u8[Bytes];
+		uint16_t u16[(Bytes + 1) / 2];
+		uint32_t u32[(Bytes + 3) / 4];
+		uint64_t u64[(Bytes + 7) / 8];
+	};
+
+	template <unsigned ElementSize>
+	__device__ __forceinline__ uint_t<ElementSize> get(unsigned i) const
+	{
+		if (ElementSize == 1) { return (uint_t<ElementSize>) u8[i]; }
+		if (ElementSize == 2) { return (uint_t<ElementSize>) u16[i]; }
+		if (ElementSize == 4) { return (uint_t<ElementSize>) u32[i]; }
+		return (uint_t<ElementSize>) u64[i];
+	}
+
+	template <unsigned ElementSize>
+	__device__ __forceinline__ void set(unsigned i, uint_t<ElementSize> x)
+	{
+		if (ElementSize == 1) { u8[i] = (uint8_t) x; }
+		else if (ElementSize == 2) { u16[i] = (uint16_t) x; }
+		else if (ElementSize == 4) { u32[i] = (uint32_t) x; }
+		else { u64[i] = (uint64_t) x; }
+	}
+};
+
+// Load Bytes bytes from a Bytes-aligned (16-aligned when Bytes >= 16) global address.
+template <unsigned Bytes>
+__device__ __forceinline__ byte_pack<Bytes> load_pack(const void* p)
+{
+	byte_pack<Bytes> r;
+	if (Bytes == 1) { r.u8[0] = load_streaming_1(p); }
+	else if (Bytes == 2) { r.u16[0] = load_streaming_2(p); }
+	else if (Bytes == 4) { r.u32[0] = load_streaming_4(p); }
+	else if (Bytes == 8) { uint2 t = load_streaming_8(p); r.u32[0] = t.x; r.u32[1] = t.y; }
+	else {
+		#pragma unroll
+		for (unsigned k = 0; k < Bytes / 16; k++) {
+			uint4 t = load_streaming_16(static_cast<const uint8_t*>(p) + 16 * k);
+			r.u32[4 * k] = t.x; r.u32[4 * k + 1] = t.y; r.u32[4 * k + 2] = t.z; r.u32[4 * k + 3] = t.w;
+		}
+	}
+	return r;
+}
+
+__device__ __forceinline__ void store_pack_16(void* p, const byte_pack<16>& v)
+{
+	store_streaming_16(p, make_uint4(v.u32[0], v.u32[1], v.u32[2], v.u32[3]));
+}
+
+// ---- warp-level scans ------------------------------------------------------------------------
+
+template <typename T>
+__device__ __forceinline__ T shuffle_up(T x, unsigned delta)
+{
+	if (sizeof(T) <= 4) { return (T) __shfl_up_sync(full_mask, (uint32_t) x, delta); }
+	else { return (T) __shfl_up_sync(full_mask, (unsigned long long) x, delta); }
+}
+
+template <typename T>
+__device__ __forceinline__ T shuffle_from(T x, unsigned lane)
+{
+	if (sizeof(T) <= 4) { return (T) __shfl_sync(full_mask, (uint32_t) x, lane); }
+	else { return (T) __shfl_sync(full_mask, (unsigned long long) x, lane); }
+}
+
+// Inclusive prefix sum across the warp's lanes (modular arithmetic in T).
+template <typename T>
+__device__ __forceinline__ T warp_inclusive_sum(T x)
+{
+	#pragma unroll
+	for (unsigned d = 1; d < warp_size; d <<= 1) {
+		T y = shuffle_up(x, d);
+		if (lane_index() >= d) { x = (T)(x + y); }
+	}
+	return x;
+}
+
+// ---- integer helpers --------------------------------------------------------------------------
+
+template <typename T>
+__host__ __device__ constexpr T div_rounding_up(T a, T b) { return (a + b - 1) / b; }
+
+template <typename T>
+__device__ __forceinline__ T minimum(T a, T b) { return a < b ? a : b; }
+
+// Per-warp slice of the block's dynamic shared memory.
+extern __shared__ __align__(16) unsigned char dynamic_shared_memory[];
+
+__device__ __forceinline__ unsigned char* warp_shared_memory(unsigned bytes_per_warp)
+{
+	return dynamic_shared_memory + (size_t) warp_index_in_block() * bytes_per_warp;
+}
+
+} // namespace device
+} // namespace giddy
+
+#endif // GIDDY_B200_KERNELS_COMMON_CUH_

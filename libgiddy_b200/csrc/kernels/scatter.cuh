@@ -1,0 +1,137 @@
+// Patching kernels: plain scatter and compressed-indices scatter.
+//
+// Both read their inputs with warp-contiguous accesses and issue the (inherently scattered)
+// element stores with several independent ones in flight per thread.  Patch targets were just
+// written by the decode kernel, so they are usually still resident in the 126 MB L2 and the
+// read-modify-write of a 32-byte sector happens there rather than in HBM.
+#pragma once
+#ifndef GIDDY_B200_KERNELS_SCATTER_CUH_
+#define GIDDY_B200_KERNELS_SCATTER_CUH_
+
+#include "common.cuh"
+
+namespace giddy {
+namespace kernels {
+
+using namespace giddy::device;
+
+// -------------------------------------------------------------------------------------------------
+// Replaces cuda::kernels::scatter::scatter, reference src/kernels/data_layout/scatter.cuh:26-46
+// (same parameter list):  target[indices[i]] = data[i]  for i < data_length.
+// -------------------------------------------------------------------------------------------------
+template <unsigned OutputIndexSize, unsigned ElementSize, unsigned InputIndexSize>
+__global__ void scatter(
+	uint_t<ElementSize>*            __restrict__  target,
+	const uint_t<ElementSize>*      __restrict__  data,
+	const uint_t<OutputIndexSize>*  __restrict__  indices,
+	size_type<InputIndexSize>                     data_length)
+{
+	constexpr unsigned unroll = GIDDY_SCATTER_UNROLL;
+	const uint64_t per_tile = (uint64_t) blockDim.x * unroll;
+	for (uint64_t tile_start = (uint64_t) blockIdx.x * per_tile; tile_start < data_length; tile_start += (uint64_t) gridDim.x * per_tile) {
+		uint_t<ElementSize> values[unroll];
+		uint_t<OutputIndexSize> positions[unroll];
+		#pragma unroll
+		for (unsigned k = 0; k < unroll; k++) {
+			const uint64_t i = tile_start + (uint64_t) k * blockDim.x + threadIdx.x;
+			if (i < data_length) { values[k] = __ldg(data + i); positions[k] = __ldg(indices + i); }
+		}
+		#pragma unroll
+		for (unsigned k = 0; k < unroll; k++) {
+			const uint64_t i = tile_start + (uint64_t) k * blockDim.x + threadIdx.x;
+			if (i < data_length) { target[positions[k]] = values[k]; }
+		}
+	}
+}
+
+namespace ci_detail {
+
+// An offset of `width_bytes` (1, 2, 4 or 8) bytes, the j-th of a run whose offsets start at `run_offsets`
+// (aligned to min(width, OutputIndexSize) bytes).
+__device__ __forceinline__ uint64_t load_offset(const uint8_t* __restrict__ run_offsets, uint64_t j, unsigned width_bytes)
+{
+	switch (width_bytes) {
+	case 1: return __ldg(run_offsets + j);
+	case 2: return __ldg(reinterpret_cast<const uint16_t*>(run_offsets) + j);
+	case 4: return __ldg(reinterpret_cast<const uint32_t*>(run_offsets) + j);
+	default: {
+		const uint32_t* words = reinterpret_cast<const uint32_t*>(run_offsets) + 2 * j;
+		return (uint64_t) __ldg(words) | ((uint64_t) __ldg(words + 1) << 32);
+	}
+	}
+}
+
+} // namespace ci_detail
+
+// -------------------------------------------------------------------------------------------------
+// Replaces cuda::kernels::scatter::compressed_indices::scatter,
+// reference src/kernels/data_layout/compressed_indices_scatter.cuh:219-271 (same parameter list).
+// Patch positions come in runs; run r has a baseline position, a per-run offset width (8/16/32/64
+// bits) and run_lengths[r] offsets stored at byte offsets_start[r] * OutputIndexSize of the offset
+// bytes; anchoring period a covers the runs [anchors[a], anchors[a+1]) and patch values from a*A.
+//   target[(OI)(baseline[r] + offset_r[j])] = data[k],  k advancing through the runs in order.
+//
+// A warp owns an anchoring period.  The metadata of 32 runs is loaded at once (one run per lane),
+// a warp scan of the run lengths locates each run's first patch value, and the runs are then
+// walked with the lanes striding over each run's patches -- so a period costs one metadata
+// round-trip per 32 runs instead of one per run (the reference reads each run's metadata serially,
+// :83-124).
+// -------------------------------------------------------------------------------------------------
+template <unsigned OutputIndexSize, unsigned ElementSize, unsigned InputIndexSize, unsigned RunLengthSize>
+__global__ void compressed_indices_scatter(
+	uint_t<ElementSize>*            __restrict__  target,
+	const uint_t<ElementSize>*      __restrict__  data,
+	const uint_t<RunLengthSize>*    __restrict__  scatter_position_run_lengths,
+	const unsigned char*            __restrict__  scatter_position_run_individual_offset_sizes,
+	const uint_t<OutputIndexSize>*  __restrict__  scatter_position_run_baseline_values,
+	const uint_t<InputIndexSize>*   __restrict__  scatter_position_run_offsets_start_positions,
+	const unsigned char*            __restrict__  scatter_position_offset_bytes,
+	const uint_t<InputIndexSize>*   __restrict__  scatter_position_anchors,
+	uint_t<InputIndexSize>                        anchoring_period,
+	uint_t<InputIndexSize>                        num_scatter_position_runs,
+	size_type<InputIndexSize>                     data_length)
+{
+	const unsigned lane = lane_index();
+	const uint64_t period_length = anchoring_period;
+	const uint64_t num_periods = ((uint64_t) data_length + period_length - 1) / period_length;
+
+	for (uint64_t period = global_warp_index(); period < num_periods; period += num_warps_in_grid()) {
+		const uint64_t first_run = __ldg(scatter_position_anchors + period);
+		const bool reaches_end = (period + 1) * period_length >= data_length;
+		const uint64_t past_last_run = reaches_end ? (uint64_t) num_scatter_position_runs : (uint64_t) __ldg(scatter_position_anchors + period + 1);
+		uint64_t next_value = period * period_length; // index into data of the next run's first patch
+
+		for (uint64_t chunk_first_run = first_run; chunk_first_run < past_last_run; chunk_first_run += warp_size) {
+			const uint64_t run = chunk_first_run + lane;
+			const bool valid = run < past_last_run;
+			const uint64_t my_length   = valid ? (uint64_t) __ldg(scatter_position_run_lengths + run) : 0;
+			const unsigned my_width    = valid ? (unsigned) __ldg(scatter_position_run_individual_offset_sizes + run) / 8 : 1;
+			const uint64_t my_baseline = valid ? (uint64_t) __ldg(scatter_position_run_baseline_values + run) : 0;
+			const uint64_t my_offsets  = valid ? (uint64_t) __ldg(scatter_position_run_offsets_start_positions + run) * OutputIndexSize : 0;
+			const uint64_t inclusive = warp_inclusive_sum(my_length);
+			const uint64_t my_first_value = next_value + (inclusive - my_length);
+			next_value += shuffle_from(inclusive, warp_size - 1);
+			const unsigned runs_in_chunk = (unsigned) minimum<uint64_t>(warp_size, past_last_run - chunk_first_run);
+
+			for (unsigned r = 0; r < runs_in_chunk; r++) {
+				const uint64_t length      = shuffle_from(my_length, r);
+				const unsigned width       = shuffle_from(my_width, r);
+				const uint64_t baseline    = shuffle_from(my_baseline, r);
+				const uint64_t first_value = shuffle_from(my_first_value, r);
+				const uint8_t* run_offsets = scatter_position_offset_bytes + shuffle_from(my_offsets, r);
+				for (uint64_t j = lane; j < length; j += warp_size) {
+					const uint64_t k = first_value + j;
+					if (k >= data_length) { break; }
+					const uint_t<OutputIndexSize> position =
+						(uint_t<OutputIndexSize>)(baseline + ci_detail::load_offset(run_offsets, j, width));
+					target[position] = __ldg(data + k);
+				}
+			}
+		}
+	}
+}
+
+} // namespace kernels
+} // namespace giddy
+
+#endif // GIDDY_B200_KERNELS_SCATTER_CUH_
