@@ -57,6 +57,12 @@ inline T required(const kernel_t::arguments_type& arguments, const char* name) {
 template <typename T>
 inline optional<T> optional_argument(const kernel_t::arguments_type& arguments, const char* name) { return ::cuda::any_cast<T>(maybe_at(arguments, name)); }
 
+/// The kernel's attributes: those the caller already has, or else ask the runtime (one driver call)
+inline device_function::attributes_t attributes_or_query(const optional<device_function::attributes_t>& known, const void* kernel)
+{
+	return known ? known.value() : device_function_t(kernel).attributes();
+}
+
 /// The configuration shared by the warp-per-unit kernels: one length unit per warp, a fixed number of warps per block
 inline void configure_warp_per_unit(launch_config_resolution_params_t& p, ::std::size_t num_units, unsigned warps_per_block)
 {
@@ -104,8 +110,9 @@ template <unsigned IndexSize, typename Uncompressed, typename Compressed, typena
 class launch_config_resolution_params_t final : public kernels::launch_config_resolution_params_t {
 public:
 	using parent = kernels::launch_config_resolution_params_t;
-	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t data_length, ::std::size_t segment_length) :
-		parent(device_properties_, device_function_t(kernel_address<IndexSize, Uncompressed, Compressed, UnaryModelFunction>()))
+	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t data_length, ::std::size_t segment_length,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes, kernel_address<IndexSize, Uncompressed, Compressed, UnaryModelFunction>()))
 	{
 		// the same preconditions as the reference, frame_of_reference.cuh:99-104
 		if (segment_length == 0) { throw ::std::invalid_argument("The segment length must be a positive number"); }
@@ -137,11 +144,11 @@ public:
 	}
 
 	launch_configuration_t resolve_launch_configuration(
-		device::properties_t device_properties, device_function::attributes_t,
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
 		::std::size_t length, ::std::size_t segment_length,
 		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
 	{
-		launch_config_resolution_params_t<IndexSize, Uncompressed, Compressed, UnaryModelFunction> params(device_properties, length, segment_length);
+		launch_config_resolution_params_t<IndexSize, Uncompressed, Compressed, UnaryModelFunction> params(device_properties, length, segment_length, optional<device_function::attributes_t>(kernel_function_attributes));
 		return kernels::resolve_launch_configuration(params, limits);
 	}
 
@@ -198,8 +205,9 @@ template <unsigned IndexSize, typename Uncompressed, typename UnaryModelFunction
 class launch_config_resolution_params_t final : public kernels::launch_config_resolution_params_t {
 public:
 	using parent = kernels::launch_config_resolution_params_t;
-	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t length_) :
-		parent(device_properties_, device_function_t(kernel_address<IndexSize, Uncompressed, UnaryModelFunction>()))
+	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t length_,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes, kernel_address<IndexSize, Uncompressed, UnaryModelFunction>()))
 	{
 		grid_construction_resolution   = thread;
 		length                         = length_;
@@ -225,10 +233,10 @@ public:
 	}
 
 	launch_configuration_t resolve_launch_configuration(
-		device::properties_t device_properties, device_function::attributes_t, ::std::size_t length,
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes, ::std::size_t length,
 		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
 	{
-		launch_config_resolution_params_t<IndexSize, Uncompressed, UnaryModelFunction> params(device_properties, length);
+		launch_config_resolution_params_t<IndexSize, Uncompressed, UnaryModelFunction> params(device_properties, length, optional<device_function::attributes_t>(kernel_function_attributes));
 		return kernels::resolve_launch_configuration(params, limits);
 	}
 
@@ -274,9 +282,9 @@ class launch_config_resolution_params_t final : public kernels::launch_config_re
 public:
 	using parent = kernels::launch_config_resolution_params_t;
 	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t uncompressed_length, ::std::size_t segment_length,
-		optional<shared_memory_size_t> dynamic_shared_mem_limit = nullopt) :
-		parent(device_properties_, device_function_t(
-			giddy_b200_run_length_encoding_kernel(UncompressedIndexSize, UncompressedSize, RunLengthSize, RunIndexSize)), dynamic_shared_mem_limit)
+		optional<shared_memory_size_t> dynamic_shared_mem_limit = nullopt,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes, giddy_b200_run_length_encoding_kernel(UncompressedIndexSize, UncompressedSize, RunLengthSize, RunIndexSize)), dynamic_shared_mem_limit)
 	{
 		if (segment_length == 0) { throw ::std::invalid_argument("The segment length must be a positive number"); }
 		detail::configure_warp_per_unit(*this, util::div_rounding_up(uncompressed_length, segment_length), GIDDY_RUNS_WARPS_PER_BLOCK);
@@ -302,12 +310,12 @@ public:
 	}
 
 	launch_configuration_t resolve_launch_configuration(
-		device::properties_t device_properties, device_function::attributes_t,
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
 		::std::size_t uncompressed_length, ::std::size_t segment_length,
 		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
 	{
 		launch_config_resolution_params_t<UncompressedIndexSize, UncompressedSize, RunLengthSize, RunIndexSize> params(
-			device_properties, uncompressed_length, segment_length, limits.dynamic_shared_memory);
+			device_properties, uncompressed_length, segment_length, limits.dynamic_shared_memory, optional<device_function::attributes_t>(kernel_function_attributes));
 		return kernels::resolve_launch_configuration(params, limits);
 	}
 
@@ -368,8 +376,9 @@ class launch_config_resolution_params_t final : public kernels::launch_config_re
 public:
 	using parent = kernels::launch_config_resolution_params_t;
 	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t uncompressed_length, ::std::size_t position_anchoring_period,
-		optional<shared_memory_size_t> dynamic_shared_mem_limit = nullopt) :
-		parent(device_properties_, device_function_t(giddy_b200_run_position_encoding_kernel(
+		optional<shared_memory_size_t> dynamic_shared_mem_limit = nullopt,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes, giddy_b200_run_position_encoding_kernel(
 			UncompressedIndexSize, UncompressedSize, PositionOffsetSize, PositionsAreRelative, RunIndexSize)), dynamic_shared_mem_limit)
 	{
 		if (position_anchoring_period == 0) { throw ::std::invalid_argument("The segment length must be a positive number"); }
@@ -399,12 +408,12 @@ public:
 	}
 
 	launch_configuration_t resolve_launch_configuration(
-		device::properties_t device_properties, device_function::attributes_t,
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
 		::std::size_t uncompressed_length, ::std::size_t segment_length,
 		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
 	{
 		launch_config_resolution_params_t<UncompressedIndexSize, UncompressedSize, PositionOffsetSize, PositionsAreRelative, RunIndexSize> params(
-			device_properties, uncompressed_length, segment_length, limits.dynamic_shared_memory);
+			device_properties, uncompressed_length, segment_length, limits.dynamic_shared_memory, optional<device_function::attributes_t>(kernel_function_attributes));
 		return kernels::resolve_launch_configuration(params, limits);
 	}
 
@@ -463,8 +472,9 @@ class launch_config_resolution_params_t final : public kernels::launch_config_re
 public:
 	using parent = kernels::launch_config_resolution_params_t;
 	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t data_length, ::std::size_t segment_length,
-		optional<shared_memory_size_t> = nullopt) :
-		parent(device_properties_, device_function_t(giddy_b200_delta_kernel(IndexSize, UncompressedSize, CompressedSize)))
+		optional<shared_memory_size_t> = nullopt,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes, giddy_b200_delta_kernel(IndexSize, UncompressedSize, CompressedSize)))
 	{
 		if (segment_length == 0) { throw ::std::invalid_argument("The segment length must be a positive number"); }
 		detail::configure_warp_per_unit(*this, util::div_rounding_up(data_length, segment_length), GIDDY_SEGMENT_WARPS_PER_BLOCK);
@@ -484,11 +494,11 @@ public:
 	}
 
 	launch_configuration_t resolve_launch_configuration(
-		device::properties_t device_properties, device_function::attributes_t,
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
 		::std::size_t length, ::std::size_t segment_length,
 		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
 	{
-		launch_config_resolution_params_t<IndexSize, UncompressedSize, CompressedSize> params(device_properties, length, segment_length);
+		launch_config_resolution_params_t<IndexSize, UncompressedSize, CompressedSize> params(device_properties, length, segment_length, nullopt, optional<device_function::attributes_t>(kernel_function_attributes));
 		return kernels::resolve_launch_configuration(params, limits);
 	}
 
@@ -542,8 +552,9 @@ public:
 	using parent = kernels::launch_config_resolution_params_t;
 	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t input_data_length /* dictionary entries */,
 		::std::size_t num_indices /* data length */, optional<bool> cache_input_data_in_shared_memory_override = nullopt,
-		optional<shared_memory_size_t> dynamic_shared_mem_limit = nullopt) :
-		parent(device_properties_, device_function_t(giddy_b200_dictionary_kernel(IndexSize, UncompressedSize, DictionaryIndexSize)), dynamic_shared_mem_limit)
+		optional<shared_memory_size_t> dynamic_shared_mem_limit = nullopt,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes, giddy_b200_dictionary_kernel(IndexSize, UncompressedSize, DictionaryIndexSize)), dynamic_shared_mem_limit)
 	{
 		const ::std::size_t dictionary_bytes = input_data_length * UncompressedSize;
 		// The reference never caches by default ("seems to mostly hurt us", gather.cuh:202-205 -- its caching
@@ -577,13 +588,13 @@ public:
 	}
 
 	launch_configuration_t resolve_launch_configuration(
-		device::properties_t device_properties, device_function::attributes_t,
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
 		::std::size_t num_dictionary_entries, ::std::size_t data_length,
 		optional<bool> cache_input_data_in_shared_mem = nullopt, optional<serialization_factor_t> serialization_factor = nullopt,
 		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
 	{
 		launch_config_resolution_params_t<IndexSize, UncompressedSize, DictionaryIndexSize> params(
-			device_properties, num_dictionary_entries, data_length, cache_input_data_in_shared_mem, limits.dynamic_shared_memory);
+			device_properties, num_dictionary_entries, data_length, cache_input_data_in_shared_mem, limits.dynamic_shared_memory, optional<device_function::attributes_t>(kernel_function_attributes));
 		return kernels::resolve_launch_configuration(params, limits, serialization_factor);
 	}
 
@@ -645,8 +656,9 @@ template <unsigned IndexSize, unsigned UncompressedSize, unsigned CompressedSize
 class launch_config_resolution_params_t final : public kernels::launch_config_resolution_params_t {
 public:
 	using parent = kernels::launch_config_resolution_params_t;
-	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t length_) :
-		parent(device_properties_, device_function_t(giddy_b200_discard_zero_bytes_fixed_kernel(IndexSize, UncompressedSize, CompressedSize)))
+	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t length_,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes, giddy_b200_discard_zero_bytes_fixed_kernel(IndexSize, UncompressedSize, CompressedSize)))
 	{
 		static_assert(UncompressedEndianness == util::endianness_t::little_endian, "only little-endian output is supported");
 		grid_construction_resolution   = thread;
@@ -678,10 +690,10 @@ public:
 	}
 
 	launch_configuration_t resolve_launch_configuration(
-		device::properties_t device_properties, device_function::attributes_t, ::std::size_t length,
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes, ::std::size_t length,
 		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
 	{
-		launch_config_resolution_params_t<IndexSize, UncompressedSize, CompressedSize, UncompressedEndianness, SerializationFactor> params(device_properties, length);
+		launch_config_resolution_params_t<IndexSize, UncompressedSize, CompressedSize, UncompressedEndianness, SerializationFactor> params(device_properties, length, optional<device_function::attributes_t>(kernel_function_attributes));
 		return kernels::resolve_launch_configuration(params, limits);
 	}
 
@@ -725,9 +737,9 @@ template <unsigned IndexSize, unsigned UncompressedSize, unsigned ElementSizesCo
 class launch_config_resolution_params_t final : public kernels::launch_config_resolution_params_t {
 public:
 	using parent = kernels::launch_config_resolution_params_t;
-	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t length_in_elements, ::std::size_t segment_length) :
-		parent(device_properties_, device_function_t(
-			giddy_b200_discard_zero_bytes_variable_kernel(IndexSize, UncompressedSize, ElementSizesContainerSize)))
+	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t length_in_elements, ::std::size_t segment_length,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes, giddy_b200_discard_zero_bytes_variable_kernel(IndexSize, UncompressedSize, ElementSizesContainerSize)))
 	{
 		if (segment_length == 0) { throw ::std::invalid_argument("The segment length must be a positive number"); }
 		detail::configure_warp_per_unit(*this, util::div_rounding_up(length_in_elements, segment_length), GIDDY_SEGMENT_WARPS_PER_BLOCK);
@@ -749,11 +761,11 @@ public:
 	}
 
 	launch_configuration_t resolve_launch_configuration(
-		device::properties_t device_properties, device_function::attributes_t,
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
 		::std::size_t length, ::std::size_t segment_length,
 		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
 	{
-		launch_config_resolution_params_t<IndexSize, UncompressedSize, ElementSizesContainerSize> params(device_properties, length, segment_length);
+		launch_config_resolution_params_t<IndexSize, UncompressedSize, ElementSizesContainerSize> params(device_properties, length, segment_length, optional<device_function::attributes_t>(kernel_function_attributes));
 		return kernels::resolve_launch_configuration(params, limits);
 	}
 
@@ -812,9 +824,9 @@ class launch_config_resolution_params_t final : public kernels::launch_config_re
 public:
 	using parent = kernels::launch_config_resolution_params_t;
 	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t uncompressed_length,
-		optional<shared_memory_size_t> = nullopt) :
-		parent(device_properties_, device_function_t(
-			giddy_b200_incidence_bitmaps_kernel(IndexSize, UncompressedSize, BitmapAlignmentInInts, UseDictionary)))
+		optional<shared_memory_size_t> = nullopt,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes, giddy_b200_incidence_bitmaps_kernel(IndexSize, UncompressedSize, BitmapAlignmentInInts, UseDictionary)))
 	{
 		const ::std::size_t bitmap_length_in_containers = util::div_rounding_up<::std::size_t>(uncompressed_length, 32);
 		detail::configure_warp_per_unit(*this,
@@ -837,10 +849,10 @@ public:
 	}
 
 	launch_configuration_t resolve_launch_configuration(
-		device::properties_t device_properties, device_function::attributes_t, ::std::size_t length,
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes, ::std::size_t length,
 		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
 	{
-		launch_config_resolution_params_t<IndexSize, UncompressedSize, BitmapAlignmentInInts, UseDictionary> params(device_properties, length);
+		launch_config_resolution_params_t<IndexSize, UncompressedSize, BitmapAlignmentInInts, UseDictionary> params(device_properties, length, nullopt, optional<device_function::attributes_t>(kernel_function_attributes));
 		return kernels::resolve_launch_configuration(params, limits);
 	}
 
@@ -890,8 +902,9 @@ template <unsigned OutputIndexSize, unsigned ElementSize, unsigned InputIndexSiz
 class launch_config_resolution_params_t final : public kernels::launch_config_resolution_params_t {
 public:
 	using parent = kernels::launch_config_resolution_params_t;
-	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t input_data_length_) :
-		parent(device_properties_, device_function_t(giddy_b200_scatter_kernel(OutputIndexSize, ElementSize, InputIndexSize)))
+	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t input_data_length_,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes, giddy_b200_scatter_kernel(OutputIndexSize, ElementSize, InputIndexSize)))
 	{
 		grid_construction_resolution   = thread;
 		length                         = input_data_length_;
@@ -917,10 +930,10 @@ public:
 	}
 
 	launch_configuration_t resolve_launch_configuration(
-		device::properties_t device_properties, device_function::attributes_t, ::std::size_t data_length,
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes, ::std::size_t data_length,
 		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
 	{
-		launch_config_resolution_params_t<OutputIndexSize, ElementSize, InputIndexSize, SerializationFactor> params(device_properties, data_length);
+		launch_config_resolution_params_t<OutputIndexSize, ElementSize, InputIndexSize, SerializationFactor> params(device_properties, data_length, optional<device_function::attributes_t>(kernel_function_attributes));
 		return kernels::resolve_launch_configuration(params, limits);
 	}
 
@@ -964,9 +977,9 @@ template <unsigned OutputIndexSize, unsigned ElementSize, unsigned InputIndexSiz
 class launch_config_resolution_params_t final : public kernels::launch_config_resolution_params_t {
 public:
 	using parent = kernels::launch_config_resolution_params_t;
-	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t input_data_length, ::std::size_t anchoring_period) :
-		parent(device_properties_, device_function_t(
-			giddy_b200_compressed_indices_scatter_kernel(OutputIndexSize, ElementSize, InputIndexSize, RunLengthSize)))
+	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t input_data_length, ::std::size_t anchoring_period,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes, giddy_b200_compressed_indices_scatter_kernel(OutputIndexSize, ElementSize, InputIndexSize, RunLengthSize)))
 	{
 		// as in the reference, compressed_indices_scatter.cuh:288-290
 		if (input_data_length == 0) { throw ::std::invalid_argument("Zero-length scatters not currently supported"); }
@@ -992,11 +1005,11 @@ public:
 	}
 
 	launch_configuration_t resolve_launch_configuration(
-		device::properties_t device_properties, device_function::attributes_t,
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
 		::std::size_t input_data_length, ::std::size_t anchoring_period,
 		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
 	{
-		launch_config_resolution_params_t<OutputIndexSize, ElementSize, InputIndexSize, RunLengthSize> params(device_properties, input_data_length, anchoring_period);
+		launch_config_resolution_params_t<OutputIndexSize, ElementSize, InputIndexSize, RunLengthSize> params(device_properties, input_data_length, anchoring_period, optional<device_function::attributes_t>(kernel_function_attributes));
 		return kernels::resolve_launch_configuration(params, limits);
 	}
 

@@ -1,0 +1,356 @@
+"""ctypes binding of libgiddy_b200.so's registry API (include/giddy_b200.h, group 1).
+
+This is the Python-side mirror of the reference's "mode iii" interface
+(examples/src/modes_of_use/factory_provided_type_erased_wrapper.cu:8-46):
+
+    kernel = produce_subclass("decompression::delta::kernel_t<4u, 8u, 4u>")
+    config = kernel.resolve_launch_configuration({"length": size_t(n), "segment_length": size_t(L)})
+    kernel.enqueue_launch(stream, config, {"decompressed": ptr(out, "u64"), ...})
+
+Argument values carry their exact static type, as with boost::any in the reference
+(src/cuda/kernel_wrapper.cuh:47-49): a mistyped argument raises BadAnyCast, a missing one
+OutOfRange, an unknown key InvalidArgument.
+
+There is no fallback: if the shared library has not been built, importing this module fails.
+"""
+import ctypes
+import os
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgiddy_b200.so")
+
+
+class GiddyError(Exception):
+    """Base of the errors raised by libgiddy_b200 (one subclass per giddy_status_t)."""
+
+
+class InvalidArgument(GiddyError, ValueError):
+    """std::invalid_argument in the reference's C++ API"""
+
+
+class OutOfRange(GiddyError, KeyError):
+    """std::out_of_range: a required named argument is missing"""
+
+
+class BadAnyCast(GiddyError, TypeError):
+    """boost::bad_any_cast: a named argument does not have exactly the expected type"""
+
+
+class LogicError(GiddyError):
+    """std::logic_error"""
+
+
+class CudaError(GiddyError, RuntimeError):
+    """cuda::runtime_error"""
+
+
+class Unsupported(GiddyError, ValueError):
+    """the kernel API was asked for a size combination which is not instantiated"""
+
+
+_STATUS_TO_ERROR = {1: InvalidArgument, 2: OutOfRange, 3: BadAnyCast, 4: LogicError, 5: CudaError, 6: Unsupported, 7: GiddyError}
+
+# giddy_type_t
+T_U8, T_U16, T_U32, T_U64, T_I8, T_I16, T_I32, T_I64, T_BOOL = range(1, 10)
+T_ARRAY_I16_1, T_ARRAY_I16_2, T_ARRAY_I32_1, T_ARRAY_I32_2 = range(10, 14)
+T_PTR, T_CONST = 0x100, 0x200
+
+_TYPE_TAGS = {
+    "u8": T_U8, "u16": T_U16, "u32": T_U32, "u64": T_U64, "i8": T_I8, "i16": T_I16, "i32": T_I32, "i64": T_I64, "bool": T_BOOL,
+    "array_i16_1": T_ARRAY_I16_1, "array_i16_2": T_ARRAY_I16_2, "array_i32_1": T_ARRAY_I32_1, "array_i32_2": T_ARRAY_I32_2,
+}
+_SIGNED = {T_I8, T_I16, T_I32, T_I64}
+_ARRAYS = {T_ARRAY_I16_1: 1, T_ARRAY_I16_2: 2, T_ARRAY_I32_1: 1, T_ARRAY_I32_2: 2}
+
+
+class _ArgValue(ctypes.Union):
+    _fields_ = [("u", ctypes.c_uint64), ("i", ctypes.c_int64), ("p", ctypes.c_void_p), ("a", ctypes.c_int32 * 2)]
+
+
+class _Arg(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("type", ctypes.c_int), ("value", _ArgValue)]
+
+
+class LaunchConfig(ctypes.Structure):
+    """giddy_launch_config_t / cuda::launch_configuration_t"""
+    _fields_ = [("grid_dimensions", ctypes.c_uint * 3), ("block_dimensions", ctypes.c_uint * 3),
+                ("dynamic_shared_memory_size", ctypes.c_uint)]
+
+    @property
+    def grid(self):
+        return self.grid_dimensions[0]
+
+    @property
+    def block(self):
+        return self.block_dimensions[0]
+
+    def __repr__(self):
+        return "LaunchConfig(grid=%d, block=%d, dynamic_shared_memory=%d)" % (self.grid, self.block, self.dynamic_shared_memory_size)
+
+
+def make_launch_config(grid, block, dynamic_shared_memory=0):
+    c = LaunchConfig()
+    c.grid_dimensions[:] = [grid, 1, 1]
+    c.block_dimensions[:] = [block, 1, 1]
+    c.dynamic_shared_memory_size = dynamic_shared_memory
+    return c
+
+
+class _Limits(ctypes.Structure):
+    _fields_ = [("has_block_size", ctypes.c_int), ("block_size", ctypes.c_uint),
+                ("has_grid_size", ctypes.c_int), ("grid_size", ctypes.c_uint),
+                ("has_dynamic_shared_memory", ctypes.c_int), ("dynamic_shared_memory", ctypes.c_uint)]
+
+
+class DeviceProperties(ctypes.Structure):
+    """giddy_device_properties_t"""
+    _fields_ = [("compute_capability_major", ctypes.c_int), ("compute_capability_minor", ctypes.c_int),
+                ("multiprocessor_count", ctypes.c_int), ("max_threads_per_block", ctypes.c_int),
+                ("max_threads_dim_x", ctypes.c_int), ("max_threads_per_multiprocessor", ctypes.c_int),
+                ("max_blocks_per_multiprocessor", ctypes.c_int), ("warp_size", ctypes.c_int),
+                ("shared_memory_per_block", ctypes.c_size_t), ("shared_memory_per_block_optin", ctypes.c_size_t),
+                ("shared_memory_per_multiprocessor", ctypes.c_size_t), ("l2_cache_size", ctypes.c_size_t),
+                ("total_global_memory", ctypes.c_size_t)]
+
+
+def b200_device_properties():
+    """The properties of a B200, for resolving launch configurations where no GPU is present."""
+    p = DeviceProperties()
+    p.compute_capability_major, p.compute_capability_minor = 10, 0
+    p.multiprocessor_count = 148
+    p.max_threads_per_block = p.max_threads_dim_x = 1024
+    p.max_threads_per_multiprocessor = 2048
+    p.max_blocks_per_multiprocessor = 32
+    p.warp_size = 32
+    p.shared_memory_per_block = 48 * 1024
+    p.shared_memory_per_block_optin = 227 * 1024
+    p.shared_memory_per_multiprocessor = 228 * 1024
+    p.l2_cache_size = 126 * 1024 * 1024
+    p.total_global_memory = 180 * 1024 ** 3
+    return p
+
+
+class FunctionAttributes(ctypes.Structure):
+    """giddy_function_attributes_t"""
+    _fields_ = [("max_threads_per_block", ctypes.c_int), ("num_regs", ctypes.c_int),
+                ("shared_size_bytes", ctypes.c_size_t), ("const_size_bytes", ctypes.c_size_t),
+                ("local_size_bytes", ctypes.c_size_t), ("max_dynamic_shared_size_bytes", ctypes.c_int),
+                ("ptx_version", ctypes.c_int), ("binary_version", ctypes.c_int)]
+
+
+def nominal_function_attributes(max_threads_per_block=1024):
+    a = FunctionAttributes()
+    a.max_threads_per_block = max_threads_per_block
+    a.max_dynamic_shared_size_bytes = 48 * 1024
+    a.ptx_version = a.binary_version = 100
+    return a
+
+
+def load_library(path=_LIB_PATH):
+    """Load a shared library exporting the registry API and declare its prototypes."""
+    if not os.path.exists(path):
+        raise ImportError(
+            "%s has not been built (run `make` at the repository root, or __graft_entry__.build()); "
+            "libgiddy_b200 has no fallback path" % path)
+    lib = ctypes.CDLL(path)
+    lib.giddy_last_error.restype = ctypes.c_char_p
+    lib.giddy_version.restype = ctypes.c_char_p
+    lib.giddy_num_registered_kernels.restype = ctypes.c_size_t
+    lib.giddy_registered_kernel_key.restype = ctypes.c_char_p
+    lib.giddy_registered_kernel_key.argtypes = [ctypes.c_size_t]
+    lib.giddy_can_produce.argtypes = [ctypes.c_char_p]
+    lib.giddy_produce_subclass.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.giddy_kernel_destroy.argtypes = [ctypes.c_void_p]
+    lib.giddy_kernel_destroy.restype = None
+    lib.giddy_kernel_key.argtypes = [ctypes.c_void_p]
+    lib.giddy_kernel_key.restype = ctypes.c_char_p
+    lib.giddy_kernel_get_device_function.argtypes = [ctypes.c_void_p]
+    lib.giddy_kernel_get_device_function.restype = ctypes.c_void_p
+    lib.giddy_kernel_resolve_launch_configuration.argtypes = [
+        ctypes.c_void_p, ctypes.POINTER(DeviceProperties), ctypes.POINTER(FunctionAttributes),
+        ctypes.POINTER(_Arg), ctypes.c_size_t, ctypes.POINTER(_Limits), ctypes.POINTER(LaunchConfig)]
+    lib.giddy_kernel_enqueue_launch.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(LaunchConfig), ctypes.POINTER(_Arg), ctypes.c_size_t]
+    lib.giddy_device_properties.argtypes = [ctypes.c_int, ctypes.POINTER(DeviceProperties)]
+    lib.giddy_function_attributes.argtypes = [ctypes.c_void_p, ctypes.POINTER(FunctionAttributes)]
+    return lib
+
+
+class Value:
+    """A named-argument value with its exact static type (the analogue of a boost::any holding a T)."""
+    __slots__ = ("tag", "value", "keepalive")
+
+    def __init__(self, tag, value, keepalive=None):
+        self.tag, self.value, self.keepalive = tag, value, keepalive
+
+    def __repr__(self):
+        return "Value(tag=0x%x, value=%r)" % (self.tag, self.value)
+
+
+def _scalar(tag):
+    def make(x):
+        return Value(tag, int(x))
+    return make
+
+
+u8, u16, u32, u64 = _scalar(T_U8), _scalar(T_U16), _scalar(T_U32), _scalar(T_U64)
+i8, i16, i32, i64 = _scalar(T_I8), _scalar(T_I16), _scalar(T_I32), _scalar(T_I64)
+size_t = u64            # size_t is unsigned long, i.e. uint64_t, on this platform
+unsigned = u32
+serialization_factor = u16  # cuda::serialization_factor_t is unsigned short
+
+
+def boolean(x):
+    return Value(T_BOOL, 1 if x else 0)
+
+
+def uint_of_size(size):
+    """A scalar constructor for util::uint_t<size>"""
+    return {1: u8, 2: u16, 4: u32, 8: u64}[size]
+
+
+def size_type_by_index_size(size):
+    """A scalar constructor for cuda::size_type_by_index_size<size> (32 bits up to 4, else 64)"""
+    return u64 if size > 4 else u32
+
+
+def coefficients(element, values):
+    """cuda::array<int16|int32, 1|2> by value (model coefficients)"""
+    values = [int(v) for v in values]
+    return Value(_TYPE_TAGS["array_%s_%d" % (element, len(values))], values)
+
+
+def _address_of(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):   # torch.Tensor
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):     # numpy.ndarray (host memory: only meaningful to a host-side library)
+        return x.ctypes.data
+    raise TypeError("cannot take the address of a %s" % type(x).__name__)
+
+
+def ptr(x, element):
+    """A T* argument; element names T ('u8', 'i16', 'array_i32_1', ...)"""
+    return Value(T_PTR | _TYPE_TAGS[element], _address_of(x), keepalive=x)
+
+
+def cptr(x, element):
+    """A const T* argument"""
+    return Value(T_PTR | T_CONST | _TYPE_TAGS[element], _address_of(x), keepalive=x)
+
+
+def _marshal(arguments):
+    items = list(arguments.items())
+    array = (_Arg * max(len(items), 1))()
+    names = []
+    for slot, (name, value) in zip(array, items):
+        if not isinstance(value, Value):
+            raise TypeError("argument %r must be wrapped with its exact type (u32(...), size_t(...), ptr(...), ...)" % name)
+        encoded = name.encode()
+        names.append(encoded)
+        slot.name = encoded
+        slot.type = value.tag
+        base = value.tag & 0xff
+        if value.tag & T_PTR:
+            slot.value.p = value.value
+        elif base in _ARRAYS:
+            for k, v in enumerate(value.value):
+                slot.value.a[k] = v
+        elif base in _SIGNED:
+            slot.value.i = value.value
+        else:
+            slot.value.u = value.value
+    return array, len(items), names
+
+
+def _stream_handle(stream):
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, int):
+        return stream
+    return stream.cuda_stream  # torch.cuda.Stream
+
+
+class Kernel:
+    """A type-erased kernel wrapper: the analogue of a std::unique_ptr<cuda::registered::kernel_t>."""
+
+    def __init__(self, library, handle):
+        self._library, self._handle = library, handle
+
+    def __del__(self):
+        if getattr(self, "_handle", None):
+            self._library.lib.giddy_kernel_destroy(self._handle)
+            self._handle = None
+
+    @property
+    def key(self):
+        return self._library.lib.giddy_kernel_key(self._handle).decode()
+
+    def get_device_function(self):
+        """The address of the wrapped __global__ function (an integer)."""
+        return self._library.lib.giddy_kernel_get_device_function(self._handle)
+
+    def attributes(self):
+        a = FunctionAttributes()
+        self._library.check(self._library.lib.giddy_function_attributes(self.get_device_function(), ctypes.byref(a)))
+        return a
+
+    def resolve_launch_configuration(self, extra_arguments, limits=None, device_properties=None, kernel_function_attributes=None):
+        """limits: dict with any of block_size, grid_size, dynamic_shared_memory.
+        device_properties / kernel_function_attributes: None means "ask the current device / the runtime"."""
+        array, count, _names = _marshal(extra_arguments)
+        c_limits = None
+        if limits:
+            c_limits = _Limits()
+            for field in ("block_size", "grid_size", "dynamic_shared_memory"):
+                if limits.get(field) is not None:
+                    setattr(c_limits, "has_" + field, 1)
+                    setattr(c_limits, field, int(limits[field]))
+        out = LaunchConfig()
+        self._library.check(self._library.lib.giddy_kernel_resolve_launch_configuration(
+            self._handle,
+            ctypes.byref(device_properties) if device_properties is not None else None,
+            ctypes.byref(kernel_function_attributes) if kernel_function_attributes is not None else None,
+            array, count, ctypes.byref(c_limits) if c_limits is not None else None, ctypes.byref(out)))
+        return out
+
+    def enqueue_launch(self, stream, launch_config, arguments):
+        """stream: None (torch's current stream), a torch.cuda.Stream, or a raw cudaStream_t value."""
+        array, count, _names = _marshal(arguments)
+        self._library.check(self._library.lib.giddy_kernel_enqueue_launch(
+            self._handle, _stream_handle(stream), ctypes.byref(launch_config), array, count))
+
+
+class Library:
+    """One loaded shared library exporting the registry API (the product, or the rebuilt reference)."""
+
+    def __init__(self, path=_LIB_PATH):
+        self.path = path
+        self.lib = load_library(path)
+
+    def check(self, status):
+        if status != 0:
+            message = self.lib.giddy_last_error().decode(errors="replace")
+            raise _STATUS_TO_ERROR.get(status, GiddyError)(message)
+
+    def version(self):
+        return self.lib.giddy_version().decode()
+
+    def registered_keys(self):
+        return [self.lib.giddy_registered_kernel_key(i).decode() for i in range(self.lib.giddy_num_registered_kernels())]
+
+    def can_produce(self, key):
+        return bool(self.lib.giddy_can_produce(key.encode()))
+
+    def produce_subclass(self, key):
+        handle = ctypes.c_void_p()
+        self.check(self.lib.giddy_produce_subclass(key.encode(), ctypes.byref(handle)))
+        return Kernel(self, handle)
+
+    def device_properties(self, device_id=-1):
+        p = DeviceProperties()
+        self.check(self.lib.giddy_device_properties(device_id, ctypes.byref(p)))
+        return p

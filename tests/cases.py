@@ -1,0 +1,381 @@
+"""Seeded test cases for every scheme: compressed inputs (numpy), parameters, the expected output
+(from the oracle) and a launcher which decodes the case on the GPU through the registry C ABI.
+
+The same cases drive
+  * tests/test_gpu_parity.py      -- product library vs the oracle, on a B200;
+  * tests/golden/make_ref_golden.py -- the rebuilt reference kernels (oracle/_ref), whose outputs'
+    digests are committed as tests/golden/ref_gpu_digests.json;
+  * tests/test_oracle_golden.py   -- the oracle vs those committed digests, on the CPU.
+
+`ref_ok` marks the cases on which the reference's kernels are well defined;
+the others are covered by the oracle alone.
+"""
+import hashlib
+
+import numpy as np
+
+from libgiddy_b200 import encode as E
+from libgiddy_b200 import schemes as S
+from oracle import giddy_oracle as O
+
+UINT, INT = E.UINT, E.INT
+
+
+class Case:
+    def __init__(self, name, scheme, inputs, params, expected, launch, ref_ok=True, output_elements=None, initial_output=None):
+        self.name, self.scheme, self.inputs, self.params = name, scheme, inputs, params
+        self.expected, self.launch, self.ref_ok = expected, launch, ref_ok
+        self.output_elements = len(expected) if output_elements is None else output_elements
+        self.initial_output = initial_output  # for the scatters: the target's contents before patching
+
+    def __repr__(self):
+        return "Case(%s)" % self.name
+
+
+def digest(array):
+    return hashlib.sha256(np.ascontiguousarray(array).tobytes()).hexdigest()
+
+
+def rng(*seed):
+    return np.random.default_rng([int(s) for s in seed])
+
+
+def random_uint(r, size, n, bits=None):
+    bits = 8 * size if bits is None else bits
+    if bits >= 64:
+        return r.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + r.integers(0, 2, n, dtype=np.uint64)
+    return r.integers(0, 1 << bits, n, dtype=np.uint64).astype(UINT[size])
+
+
+def run_case_on_gpu(case, library=None, limits=None):
+    """Copy the case's inputs to the current CUDA device, decode, and return the output as numpy."""
+    import torch
+    device = torch.device("cuda")
+    tensors = {k: torch.from_numpy(_as_torch_compatible(v)).to(device) for k, v in case.inputs.items()}
+    itemsize = case.expected.dtype.itemsize
+    if case.initial_output is not None:
+        out = torch.from_numpy(_as_torch_compatible(case.initial_output)).to(device)
+    else:
+        # poison the output (plus a guard zone) so that unwritten or over-written elements show up
+        out = torch.full((case.output_elements + 64,), 0x5A, dtype=_torch_int(itemsize), device=device)
+    case.launch(out, tensors, library, limits)
+    torch.cuda.synchronize()
+    result = out.cpu().numpy().view(case.expected.dtype)
+    if case.initial_output is None:
+        guard = result[case.output_elements:]
+        assert (guard.view(np.uint8) == 0x5A).all(), "%s: wrote past the end of the output" % case.name
+        result = result[:case.output_elements]
+    return result
+
+
+def _torch_int(itemsize):
+    import torch
+    return {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[itemsize]
+
+
+def _as_torch_compatible(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype.kind == "u" and a.dtype.itemsize > 1:
+        return a.view(INT[a.dtype.itemsize])
+    return a
+
+
+# ---- per-scheme case builders --------------------------------------------------------------------
+
+def for_case(seed, n, L, U, C, model, I=4, MI=4):
+    r = rng(1, seed, n, L, U, C)
+    num_segments = E.num_segments(n, L)
+    dim = 2 if model == "linear" else 1
+    coefficients = r.integers(-(1 << 30), 1 << 30, (num_segments, dim), dtype=np.int64).astype(np.int32)
+    if model == "linear":
+        coefficients[:, 1] = r.integers(-1000, 1000, num_segments)
+    compressed = r.integers(-(1 << (8 * C - 1)), 1 << (8 * C - 1), n, dtype=np.int64).astype(INT[C])
+    expected = O.frame_of_reference(compressed, coefficients, n, L, U, model, MI)
+
+    def launch(out, t, library, limits):
+        S.frame_of_reference(out, t["compressed_input"], t["segment_model_coefficients"], n, L, uncompressed_size=U, compressed_size=C,
+                             model=model, index_size=I, model_index_size=MI, library=library, limits=limits)
+    # reference: L must be >= the block's thread count for its one-segment-per-block path, or divide it
+    return Case("for-%s-I%d-U%d-C%d-MI%d-n%d-L%d" % (model, I, U, C, MI, n, L), "frame_of_reference",
+                {"compressed_input": compressed, "segment_model_coefficients": coefficients}, dict(n=n, L=L), expected, launch,
+                ref_ok=(n % L == 0 and (L >= 1024 or 1024 % L == 0)))
+
+
+def model_case(seed, n, U, model, I=4):
+    r = rng(2, seed, n, U)
+    dim = 2 if model == "linear" else 1
+    coefficients = r.integers(-(1 << (8 * U - 2)), 1 << (8 * U - 2), dim, dtype=np.int64)
+    if model == "linear":
+        coefficients[1] = r.integers(-300, 300)
+    expected = O.model(coefficients, n, U, model, I)
+
+    def launch(out, t, library, limits):
+        S.model(out, [int(c) for c in coefficients], n, uncompressed_size=U, model=model, index_size=I, library=library, limits=limits)
+    return Case("model-%s-I%d-U%d-n%d" % (model, I, U, n), "model", {}, dict(n=n), expected, launch)
+
+
+def _random_runs_column(r, n, U, mean_run, value_bits=None):
+    """A column of runs with lengths uniform in [1, 2*mean_run - 1]."""
+    lengths = r.integers(1, 2 * mean_run, max(2 * n // mean_run + 16, 16))
+    lengths = lengths[: np.searchsorted(np.cumsum(lengths), n) + 1]
+    values = random_uint(r, U, len(lengths), value_bits)
+    # make sure adjacent runs differ so the encoder reproduces them (flip the low bit where they do not)
+    same = np.flatnonzero(values[1:] == values[:-1]) + 1
+    values[same] ^= UINT[U](1)
+    same = np.flatnonzero(values[1:] == values[:-1]) + 1
+    values[same] ^= UINT[U](2)
+    return np.repeat(values, lengths)[:n]
+
+
+def rle_case(seed, n, L, U, RL, I=4, mean_run=16, max_run_length=None):
+    r = rng(3, seed, n, L, U, RL)
+    column = _random_runs_column(r, n, U, mean_run)
+    enc = E.run_length_encode(column, L, RL, I, max_run_length)
+    expected = O.run_length_encoding(enc["run_data"], enc["run_lengths"], enc["position_anchors"], enc["intra_run_anchor_offsets"], L, n)
+    assert (expected == column).all()
+    num_runs = len(enc["run_data"])
+
+    def launch(out, t, library, limits):
+        S.run_length_encoding(out, t["run_data"], t["run_lengths"], t["position_anchors"], t["intra_run_anchor_offsets"],
+                              L, E.num_segments(n, L), num_runs, n, uncompressed_size=U, run_length_size=RL, index_size=I,
+                              library=library, limits=limits)
+    per_write = max(1, 4 // U)
+    return Case("rle-I%d-U%d-RL%d-n%d-L%d-run%d" % (I, U, RL, n, L, mean_run), "run_length_encoding", enc, dict(n=n, L=L), expected, launch,
+                ref_ok=(L * U >= 4 and L % per_write == 0 and n % per_write == 0))
+
+
+def rpe_case(seed, n, L, U, PO, relative, I=4, mean_run=16, avoid_boundary_runs=False):
+    r = rng(4, seed, n, L, U, PO)
+    column = _random_runs_column(r, n, U, mean_run)
+    if avoid_boundary_runs:  # make no run begin exactly on a segment boundary (reference quirk E4)
+        boundaries = np.arange(L, n, L)
+        column[boundaries] = column[boundaries - 1]
+    enc = E.run_position_encode(column, L, PO, relative, I)
+    expected = O.run_position_encoding(enc["run_data"], enc["run_start_positions"], enc["position_anchors"], L, n, relative)
+    assert (expected == column).all()
+    num_runs = len(enc["run_data"])
+
+    def launch(out, t, library, limits):
+        S.run_position_encoding(out, t["run_data"], t["run_start_positions"], t["position_anchors"], L, E.num_segments(n, L), num_runs, n,
+                                uncompressed_size=U, position_offset_size=PO, relative=relative, index_size=I, library=library, limits=limits)
+    per_write = max(1, 4 // U)
+    # reference: E14 -- all lanes of its 64-thread blocks must run the same number of iterations
+    return Case("rpe-%s-I%d-U%d-PO%d-n%d-L%d-run%d" % ("rel" if relative else "abs", I, U, PO, n, L, mean_run), "run_position_encoding",
+                enc, dict(n=n, L=L), expected, launch,
+                ref_ok=(L % (64 * per_write) == 0 and n % L == 0 and (avoid_boundary_runs or not relative)))
+
+
+def delta_case(seed, n, L, U, C, I=4):
+    r = rng(5, seed, n, L, U, C)
+    deltas = random_uint(r, C, n)
+    base = int(random_uint(r, U, 1)[0])
+    column = (np.cumsum(deltas.astype(np.uint64), dtype=np.uint64) + np.uint64(base)).astype(UINT[U])
+    enc = E.delta_encode(column, L, C, base)
+    expected = O.delta(enc["compressed_input"], enc["anchor_values"], n, L)
+    assert (expected == column).all()
+
+    def launch(out, t, library, limits):
+        S.delta(out, t["compressed_input"], t["anchor_values"], n, L, uncompressed_size=U, compressed_size=C, index_size=I,
+                library=library, limits=limits)
+    return Case("delta-I%d-U%d-C%d-n%d-L%d" % (I, U, C, n, L), "delta", enc, dict(n=n, L=L), expected, launch,
+                ref_ok=(L >= 1024 and L % 1024 == 0))
+
+
+def dictionary_case(seed, n, U, DI, num_entries, I=4, cache=None):
+    r = rng(6, seed, n, U, DI, num_entries)
+    entries = random_uint(r, U, num_entries)
+    indices = r.integers(0, num_entries, n, dtype=np.uint64).astype(UINT[DI])
+    expected = O.dictionary(indices, entries, n)
+
+    def launch(out, t, library, limits):
+        S.dictionary(out, t["compressed_input"], t["dictionary_entries"], n, num_entries, uncompressed_size=U, dictionary_index_size=DI,
+                     index_size=I, cache_in_shared_memory=cache, library=library, limits=limits)
+    return Case("dict-I%d-U%d-DI%d-D%d-n%d-cache%s" % (I, U, DI, num_entries, n, cache), "dictionary",
+                {"compressed_input": indices, "dictionary_entries": entries}, dict(n=n), expected, launch)
+
+
+def dzbf_case(seed, n, U, C, I=4):
+    r = rng(7, seed, n, U, C)
+    compressed = random_uint(r, C, n)
+    expected = O.discard_zero_bytes_fixed(compressed, n, U)
+
+    def launch(out, t, library, limits):
+        S.discard_zero_bytes_fixed(out, t["compressed_input"], n, uncompressed_size=U, compressed_size=C, index_size=I, library=library, limits=limits)
+    return Case("dzbf-I%d-U%d-C%d-n%d" % (I, U, C, n), "discard_zero_bytes_fixed", {"compressed_input": compressed}, dict(n=n), expected, launch)
+
+
+def dzbv_case(seed, n, L, U, CS, bits, min_size, I=4):
+    r = rng(8, seed, n, L, U, CS, bits)
+    max_size = min(U, min_size + (1 << bits) - 1)
+    widths = r.integers(min_size, max_size + 1, n)
+    column = np.zeros(n, dtype=UINT[U])
+    raw = random_uint(r, U, n)
+    for w in range(1, U + 1):
+        mask = widths == w
+        column[mask] = raw[mask] >> UINT[U](8 * (U - w)) if w < U else raw[mask]
+    enc = E.discard_zero_bytes_variable_encode(column, L, CS, bits, min_size, I)
+    sizes = enc.pop("element_sizes")
+    # the kernels may read the aligned word holding the stream's last byte: keep the buffer word-padded
+    enc["compressed_data"] = np.concatenate((enc["compressed_data"], np.zeros(8, np.uint8)))
+    expected = O.discard_zero_bytes_variable(enc["compressed_data"], enc["packed_element_sizes"], enc["position_anchors"], L, n, min_size, bits, U)
+    assert (expected == column).all(), (sizes[:8], column[:8], expected[:8])
+
+    def launch(out, t, library, limits):
+        S.discard_zero_bytes_variable(out, t["compressed_data"], t["packed_element_sizes"], t["position_anchors"], L, n, min_size, bits,
+                                      uncompressed_size=U, container_size=CS, index_size=I, library=library, limits=limits)
+    return Case("dzbv-I%d-U%d-CS%d-b%d-m%d-n%d-L%d" % (I, U, CS, bits, min_size, n, L), "discard_zero_bytes_variable", enc, dict(n=n, L=L),
+                expected, launch, ref_ok=(n % L == 0))
+
+
+def bitmaps_case(seed, n, U, K, use_dictionary=True, I=4, alignment=2):
+    r = rng(9, seed, n, U, K)
+    indices = r.integers(0, K, n)
+    bitmaps, bitmap_length = E.incidence_bitmaps_encode(indices, K, alignment)
+    # elements past n in the last container belong to no bitmap: undefined in the reference; make them bitmap 0
+    tail = bitmap_length * 32 - n
+    if tail:
+        bitmaps[bitmap_length - 1] |= np.uint32(((1 << tail) - 1) << (32 - tail))
+    entries = random_uint(r, U, K) if use_dictionary else np.zeros(1, dtype=UINT[U])
+    expected = O.incidence_bitmaps(bitmaps, entries, bitmap_length, K, U, alignment, use_dictionary)
+
+    def launch(out, t, library, limits):
+        S.incidence_bitmaps(out, t["incidence_bitmaps"], t["dictionary_entries"], n, bitmap_length, K, uncompressed_size=U,
+                            alignment_in_ints=alignment, use_dictionary=use_dictionary, index_size=I, library=library, limits=limits)
+    # reference quirk E8: the last warp reads past bitmap_length unless it is a multiple of 32 containers
+    return Case("bitmaps-I%d-U%d-K%d-dict%d-n%d" % (I, U, K, use_dictionary, n), "incidence_bitmaps",
+                {"incidence_bitmaps": bitmaps, "dictionary_entries": entries}, dict(n=n), expected, launch,
+                ref_ok=(bitmap_length % 32 == 0))
+
+
+def scatter_case(seed, target_length, p, U, OI, II):
+    r = rng(10, seed, target_length, p, U, OI, II)
+    target = random_uint(r, U, target_length)
+    positions = np.sort(r.choice(target_length, p, replace=False)).astype(UINT[OI])
+    r.shuffle(positions)
+    data = random_uint(r, U, p)
+    expected = O.scatter(target.copy(), data, positions)
+
+    def launch(out, t, library, limits):
+        S.scatter(out, t["data"], t["indices"], p, element_size=U, output_index_size=OI, input_index_size=II, library=library, limits=limits)
+    return Case("scatter-OI%d-U%d-II%d-p%d" % (OI, U, II, p), "scatter", {"data": data, "indices": positions}, dict(p=p), expected, launch,
+                initial_output=target)
+
+
+def ci_scatter_case(seed, target_length, p, U, OI, II, A, max_run_length=64, widths=(8, 16, 32, 64)):
+    r = rng(11, seed, target_length, p, U, OI, II, A)
+    target = random_uint(r, U, target_length)
+    positions = np.sort(r.choice(target_length, p, replace=False))
+    data = random_uint(r, U, p)
+    enc = E.compressed_indices_encode(positions, A, OI, II, max_run_length, widths)
+    expected = O.compressed_indices_scatter(target.copy(), data, enc["scatter_position_run_lengths"],
+                                            enc["scatter_position_run_individual_offset_sizes"], enc["scatter_position_run_baseline_values"],
+                                            enc["scatter_position_run_offsets_start_pos"], enc["scatter_position_offset_bytes"],
+                                            enc["scatter_position_anchors"], A)
+    check = target.copy()
+    check[positions] = data
+    assert (expected == check).all()
+    num_runs = len(enc["scatter_position_run_lengths"])
+    inputs = dict(enc, data_to_scatter=data)
+    inputs["scatter_position_offset_bytes"] = np.concatenate((enc["scatter_position_offset_bytes"], np.zeros(8, np.uint8)))
+
+    def launch(out, t, library, limits):
+        S.compressed_indices_scatter(out, t["data_to_scatter"], t["scatter_position_run_lengths"],
+                                     t["scatter_position_run_individual_offset_sizes"], t["scatter_position_run_baseline_values"],
+                                     t["scatter_position_run_offsets_start_pos"], t["scatter_position_offset_bytes"],
+                                     t["scatter_position_anchors"], A, num_runs, p, element_size=U, output_index_size=OI,
+                                     input_index_size=II, library=library, limits=limits)
+    return Case("ciscatter-OI%d-U%d-II%d-p%d-A%d" % (OI, U, II, p, A), "compressed_indices_scatter", inputs, dict(p=p, A=A), expected, launch,
+                initial_output=target)
+
+
+# ---- the case list ---------------------------------------------------------------------------------
+
+def all_cases():
+    """Every registered type combination of every scheme at least once, plus ragged / tiny / odd shapes."""
+    cases = []
+    # Frame of Reference (8 keys)
+    for (I, U, C, model, MI) in [(4, 2, 1, "linear", 4), (4, 4, 1, "linear", 4), (4, 4, 2, "linear", 4), (8, 4, 2, "linear", 4),
+                                 (8, 4, 2, "linear", 8), (4, 2, 1, "constant", 4), (4, 4, 1, "constant", 4), (4, 4, 2, "constant", 4)]:
+        cases.append(for_case(0, 8 * 2048, 2048, U, C, model, I, MI))
+        cases.append(for_case(1, 40000 + 13, 1020, U, C, model, I, MI))  # ragged tail, L not a power of 2
+    cases.append(for_case(2, 1000, 4, 2, 1, "linear"))       # segments shorter than a vector
+    cases.append(for_case(3, 3, 4, 4, 2, "constant"))        # shorter than one segment
+    cases.append(for_case(4, 1 << 20, 4096, 4, 2, "constant"))
+    # Model (5 keys)
+    for (I, U, model) in [(4, 2, "linear"), (4, 4, "linear"), (8, 4, "linear"), (4, 2, "constant"), (4, 4, "constant")]:
+        cases.append(model_case(0, 100000 + 7, U, model, I))
+    cases.append(model_case(1, 5, 4, "linear"))
+    # RLE (18 keys)
+    for (I, U, RL) in [(4, u, rl) for rl in (1, 2, 4) for u in (1, 2, 4, 8)] + [(8, 4, 1), (8, 4, 2), (8, 4, 4), (8, 1, 8), (8, 4, 8), (8, 8, 8)]:
+        cases.append(rle_case(0, 64 * 1024, 1024, U, RL, I))
+    cases.append(rle_case(1, 50000 + 3, 1000, 4, 2))                      # ragged tail; L not a multiple of the tile
+    cases.append(rle_case(2, 70000, 4096, 4, 2, mean_run=2))              # short runs, several tiles per segment
+    cases.append(rle_case(3, 70000, 2048, 8, 1, mean_run=300))            # runs longer than the length type allows: split runs
+    cases.append(rle_case(4, 100000, 1024, 4, 2, mean_run=5000))          # runs spanning many segments
+    cases.append(rle_case(5, 9000, 1024, 1, 1, mean_run=1))               # every element its own run
+    cases.append(rle_case(6, 7, 1024, 4, 2))                              # a single partial segment
+    cases.append(rle_case(7, 40000, 36, 2, 2, mean_run=7))                # tiny segments
+    cases.append(rle_case(8, 1 << 20, 1024, 4, 2))
+    # RPE (10 keys)
+    for (I, U, PO, rel) in [(4, u, 2, True) for u in (1, 2, 4, 8)] + [(8, 4, 2, True)] + [(4, u, 4, False) for u in (1, 2, 4, 8)] + [(8, 4, 8, False)]:
+        cases.append(rpe_case(0, 64 * 1024, 1024, U, PO, rel, I, avoid_boundary_runs=rel))
+    cases.append(rpe_case(1, 50000 + 3, 1000, 4, 4, False))
+    cases.append(rpe_case(2, 70000, 4096, 4, 4, False, mean_run=2))
+    cases.append(rpe_case(3, 70000, 1024, 4, 2, True, mean_run=3))        # relative, runs beginning on segment boundaries
+    cases.append(rpe_case(4, 100000, 1024, 8, 4, False, mean_run=5000))
+    cases.append(rpe_case(5, 1 << 20, 1024, 4, 4, False, mean_run=64))
+    # Delta (12 keys)
+    for I in (4, 8):
+        for (U, C) in [(2, 1), (4, 1), (4, 2), (8, 1), (8, 2), (8, 4)]:
+            cases.append(delta_case(0, 32 * 1024, 1024, U, C, I))
+    cases.append(delta_case(1, 50000 + 5, 1000, 8, 4))                    # ragged; L % E == 0
+    cases.append(delta_case(2, 50000 + 5, 999, 8, 4))                     # L not a multiple of the vector width
+    cases.append(delta_case(3, 10000, 24, 4, 2))                          # segments shorter than a row
+    cases.append(delta_case(4, 300000, 100000, 8, 4))                     # long segments
+    cases.append(delta_case(5, 1 << 20, 1024, 8, 4))
+    # Dictionary (20 keys)
+    for I in (4, 8):
+        for (U, DI) in [(1, 1), (2, 1), (2, 2), (4, 1), (4, 2), (4, 4), (8, 1), (8, 2), (8, 4), (8, 8)]:
+            cases.append(dictionary_case(0, 100000 + 11, U, DI, min(1 << (8 * DI), 1000), I))
+    cases.append(dictionary_case(1, 1 << 20, 8, 1, 256, cache=True))
+    cases.append(dictionary_case(2, 1 << 20, 8, 1, 256, cache=False))
+    cases.append(dictionary_case(3, 1 << 18, 4, 2, 40000, cache=True))    # 160 KB dictionary in shared memory
+    cases.append(dictionary_case(4, 9, 8, 1, 3))
+    # DZB fixed (12 keys)
+    for I in (4, 8):
+        for (U, C) in [(2, 1), (4, 1), (4, 2), (8, 1), (8, 2), (8, 4)]:
+            cases.append(dzbf_case(0, 100000 + 9, U, C, I))
+    # DZB variable (9 keys)
+    for (I, U, CS) in [(4, 2, 4), (4, 4, 4), (4, 8, 4), (8, 2, 4), (8, 4, 4), (8, 8, 4), (4, 2, 8), (4, 4, 8), (4, 8, 8)]:
+        bits, min_size = (1, 1) if U == 2 else ((2, 1) if U == 4 else (3, 1))
+        cases.append(dzbv_case(0, 32 * 1024, 1024, U, CS, bits, min_size, I))
+    cases.append(dzbv_case(1, 50000 + 3, 1000, 4, 4, 2, 1))               # ragged tail
+    cases.append(dzbv_case(2, 50000, 1001, 4, 4, 2, 1))                   # unaligned segments
+    cases.append(dzbv_case(3, 40000, 1024, 4, 4, 3, 0))                   # 3-bit fields (10 per container), zero-size elements
+    cases.append(dzbv_case(4, 40000, 1024, 8, 8, 4, 0))
+    cases.append(dzbv_case(5, 1 << 20, 1024, 4, 4, 2, 1))
+    # Incidence bitmaps (5 keys)
+    for (U, use_dictionary) in [(1, True), (2, True), (4, True), (8, True), (1, False)]:
+        cases.append(bitmaps_case(0, 64 * 1024, U, 16, use_dictionary))
+    cases.append(bitmaps_case(1, 100000 + 21, 4, 5))                      # ragged
+    cases.append(bitmaps_case(2, 1 << 18, 4, 200))
+    cases.append(bitmaps_case(3, 40, 4, 2))
+    cases.append(bitmaps_case(4, 1 << 16, 8, 1))                          # a single bitmap
+    # Scatter (32 keys) and compressed-indices scatter (32 keys)
+    for OI in (4, 8):
+        for U in (1, 2, 4, 8):
+            for II in (1, 2, 4, 8):
+                p = min(2000, (1 << (8 * II)) - 1)
+                cases.append(scatter_case(0, 200000, p, U, OI, II))
+                A = min(1024, max(p // 3, 16))
+                if A < (1 << (8 * II)):
+                    cases.append(ci_scatter_case(0, 200000, p, U, OI, II, A, max_run_length=min(50, (1 << (8 * II)) - 1)))
+    cases.append(scatter_case(1, 1 << 22, 41943, 8, 4, 4))
+    cases.append(ci_scatter_case(1, 1 << 22, 41943, 4, 4, 4, 1024))
+    cases.append(ci_scatter_case(2, 1 << 22, 3000, 8, 8, 4, 1000, widths=(8, 16, 32)))
+    return cases
+
+
+def small_cases():
+    """A subset which finishes quickly: used for host-side (oracle-only) checks."""
+    return [c for c in all_cases() if c.output_elements <= 300000]

@@ -1,0 +1,45 @@
+"""Parity tests proper: every scheme, decoded on the GPU through the registry C ABI, must match the
+oracle bit for bit (integer / byte work: no tolerance).  Run on a B200 with `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+ALL_CASES = cases.all_cases()
+
+
+def _mismatch_report(case, got):
+    bad = np.flatnonzero(got != case.expected)
+    first = bad[:8]
+    return "%s: %d of %d elements differ; first at %s: got %s, expected %s" % (
+        case.name, len(bad), len(got), first.tolist(), got[first].tolist(), case.expected[first].tolist())
+
+
+@pytest.mark.parametrize("case", ALL_CASES, ids=lambda c: c.name)
+def test_matches_oracle(case, library):
+    got = cases.run_case_on_gpu(case, library)
+    assert got.shape == case.expected.shape
+    assert (got == case.expected).all(), _mismatch_report(case, got)
+
+
+# Kernels must be correct under any launch configuration the resolver can be limited to, not just
+# the preferred one ("limits ... used for testing", reference resolve_launch_configuration.h:17).
+LIMITED = [c for c in ALL_CASES if c.output_elements <= 120000][::3]
+
+
+@pytest.mark.parametrize("limits", [{"block_size": 32}, {"block_size": 96}, {"block_size": 1024}], ids=lambda l: "block%d" % l["block_size"])
+@pytest.mark.parametrize("case", LIMITED, ids=lambda c: c.name)
+def test_matches_oracle_under_block_size_limits(case, limits, library):
+    got = cases.run_case_on_gpu(case, library, limits)
+    assert (got == case.expected).all(), _mismatch_report(case, got)
+
+
+@pytest.mark.parametrize("case", [c for c in ALL_CASES if c.ref_ok], ids=lambda c: c.name)
+def test_matches_reference_kernels(case, library, reference_library):
+    """Drop-in check: same inputs, same named arguments, through the same C ABI, into the reference's
+    own kernels rebuilt for sm_100a -- outputs must be identical."""
+    ours = cases.run_case_on_gpu(case, library)
+    theirs = cases.run_case_on_gpu(case, reference_library)
+    assert (ours == theirs).all(), _mismatch_report(case, theirs)
