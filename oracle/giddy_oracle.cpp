@@ -134,16 +134,16 @@ int rle_decompress(void* out_, const void* run_data_, const void* run_lengths_,
 		uint64_t start = (uint64_t) s * L;
 		if (start >= n) { continue; }
 		uint64_t len = ((uint64_t) s + 1 == S) ? n - start : L;
+		// walk the runs from the anchor's, filling each run's part of the segment
 		uint64_t run = anchors[s];
 		uint64_t run_end = (uint64_t) run_lengths[run] - intra[s]; // segment-relative end of the current run
-		uint_t<U> v = run_data[run];
-		for (uint64_t p = 0; p < len; p++) {
-			while (run_end <= p && run + 1 < R) {
-				run++;
-				run_end += run_lengths[run];
-				v = run_data[run];
-			}
-			out[start + p] = v;
+		uint64_t p = 0;
+		while (p < len) {
+			if (run + 1 >= R || run_end > len) { run_end = len; } // the last run extends to the end of the column
+			const uint_t<U> v = run_data[run];
+			for (uint64_t q = p; q < run_end; q++) { out[start + q] = v; }
+			p = run_end;
+			if (p < len) { run++; run_end += run_lengths[run]; }
 		}
 	}
 	return 0;
@@ -187,10 +187,15 @@ int rpe_decompress(void* out_, const void* run_data_, const void* run_starts_, c
 			past_last = next + (next_run_begins_before_next_segment ? 1 : 0);
 		}
 		uint64_t base = relative ? 0 : seg_start;
-		uint64_t run = first;
-		for (uint64_t p = 0; p < len; p++) {
-			while (run + 1 < past_last && (uint64_t) starts[run + 1] <= base + p) { run++; }
-			out[seg_start + p] = run_data[run];
+		uint64_t p = 0;
+		for (uint64_t run = first; p < len; run++) {
+			// this run covers positions up to the next run's start (or the segment's end)
+			uint64_t end = (run + 1 < past_last) ? (uint64_t) starts[run + 1] - base : len;
+			if (end > len) { end = len; }
+			const uint_t<U> v = run_data[run];
+			for (uint64_t q = p; q < end; q++) { out[seg_start + q] = v; }
+			if (end > p) { p = end; }
+			if (run + 1 >= past_last) { break; }
 		}
 	}
 	return 0;
