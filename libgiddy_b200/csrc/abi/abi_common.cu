@@ -1,6 +1,8 @@
 // C ABI: error reporting, device / function queries, launch-by-pointer.
 #include "abi_internal.hpp"
 #include <cstring>
+#include <map>
+#include <mutex>
 
 namespace giddy {
 namespace abi {
@@ -37,6 +39,14 @@ giddy_status_t giddy_device_properties(int device_id, giddy_device_properties_t*
 		error = cudaGetDevice(&device_id);
 		if (error != cudaSuccess) { return fail_cuda(error, "cudaGetDevice"); }
 	}
+	// cudaGetDeviceProperties costs milliseconds; a device's properties do not change, so ask once
+	static std::mutex cache_mutex;
+	static std::map<int, giddy_device_properties_t> cache;
+	{
+		std::lock_guard<std::mutex> lock(cache_mutex);
+		auto it = cache.find(device_id);
+		if (it != cache.end()) { *out = it->second; return GIDDY_SUCCESS; }
+	}
 	cudaDeviceProp p;
 	error = cudaGetDeviceProperties(&p, device_id);
 	if (error != cudaSuccess) { return fail_cuda(error, "cudaGetDeviceProperties"); }
@@ -54,6 +64,10 @@ giddy_status_t giddy_device_properties(int device_id, giddy_device_properties_t*
 	out->shared_memory_per_multiprocessor = p.sharedMemPerMultiprocessor;
 	out->l2_cache_size = (size_t) p.l2CacheSize;
 	out->total_global_memory = p.totalGlobalMem;
+	{
+		std::lock_guard<std::mutex> lock(cache_mutex);
+		cache[device_id] = *out;
+	}
 	return GIDDY_SUCCESS;
 }
 

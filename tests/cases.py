@@ -57,7 +57,7 @@ def run_case_on_gpu(case, library=None, limits=None):
         out = torch.from_numpy(_as_torch_compatible(case.initial_output)).to(device)
     else:
         # poison the output (plus a guard zone) so that unwritten or over-written elements show up
-        out = torch.full((case.output_elements + 64,), 0x5A, dtype=_torch_int(itemsize), device=device)
+        out = torch.full(((case.output_elements + 64) * itemsize,), 0x5A, dtype=torch.uint8, device=device).view(_torch_int(itemsize))
     case.launch(out, tensors, library, limits)
     torch.cuda.synchronize()
     result = out.cpu().numpy().view(case.expected.dtype)
