@@ -29,12 +29,33 @@ def _check_size(tensor, size, name):
         raise ValueError("%s: expected elements of %d bytes, got %d" % (name, size, tensor.element_size()))
 
 
+_kernels = {}         # (library path, key) -> Kernel: wrappers are stateless, so one instance per key serves all calls
+_configurations = {}  # (library path, key, resolve arguments, limits) -> LaunchConfig, per current device
+
+
 def _run(library, key, resolve_arguments, launch_arguments, stream, limits, device_properties=None):
     library = library or default_library()
-    kernel = library.produce_subclass(key)
-    config = kernel.resolve_launch_configuration(resolve_arguments, limits=limits, device_properties=device_properties)
+    kernel = _kernels.get((library.path, key))
+    if kernel is None:
+        kernel = _kernels[(library.path, key)] = library.produce_subclass(key)
+    signature = (library.path, key, tuple(sorted((k, v.tag, v.value) for k, v in resolve_arguments.items())),
+                 tuple(sorted(limits.items())) if limits else None, _current_device())
+    config = _configurations.get(signature)
+    if config is None:
+        config = kernel.resolve_launch_configuration(resolve_arguments, limits=limits, device_properties=device_properties)
+        if len(_configurations) > 4096:
+            _configurations.clear()
+        _configurations[signature] = config
     kernel.enqueue_launch(stream, config, launch_arguments)
     return config
+
+
+def _current_device():
+    try:
+        import torch
+        return torch.cuda.current_device()
+    except Exception:
+        return -1
 
 
 # ---- keys -----------------------------------------------------------------
