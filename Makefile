@@ -52,7 +52,7 @@ $(LIB): $(ABI_OBJS) $(HOST_OBJS)
 oracle: $(ORACLE_LIB)
 
 $(ORACLE_LIB): oracle/giddy_oracle.cpp
-	$(CXX) -std=c++17 -O3 -march=native -fopenmp -fPIC -shared -Wall -o $@ $<
+	$(CXX) -std=c++17 -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -Wall -o $@ $<
 
 ref:
 	bash oracle/build_ref.sh

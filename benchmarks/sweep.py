@@ -51,7 +51,7 @@ def workloads(log2_n):
     return w
 
 
-def time_case(torch, cases, case, library, repeats):
+def time_case(torch, cases, case, library, repeats, single_launch=False):
     device = torch.device("cuda")
     tensors = {k: torch.from_numpy(cases._as_torch_compatible(v)).to(device) for k, v in case.inputs.items()}
     itemsize = case.expected.dtype.itemsize
@@ -61,6 +61,8 @@ def time_case(torch, cases, case, library, repeats):
         out = torch.zeros(case.output_elements + 64, dtype=cases._torch_int(itemsize), device=device)
     case.launch(out, tensors, library, None)
     torch.cuda.synchronize()
+    if single_launch:  # profiling mode (under ncu): exactly one launch per workload
+        return float("nan"), True
     got = out.cpu().numpy().view(case.expected.dtype)[:case.output_elements]
     correct = bool((got == case.expected).all())
     for _ in range(3):
@@ -82,6 +84,7 @@ def main():
     p.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     p.add_argument("--only", default="")
     p.add_argument("--no-reference", action="store_true")
+    p.add_argument("--single-launch", action="store_true", help="one untimed launch per workload (for ncu captures)")
     args = p.parse_args()
 
     import torch
@@ -107,7 +110,10 @@ def main():
         out_bytes = (patch_elements if is_scatter else case.output_elements) * case.expected.dtype.itemsize
         algorithmic = input_bytes(case) + out_bytes
         row = {"workload": name, "case": case.name, "output_bytes": out_bytes, "algorithmic_bytes": algorithmic}
-        seconds, correct = time_case(torch, cases, case, product, args.repeats)
+        seconds, correct = time_case(torch, cases, case, product, args.repeats, args.single_launch)
+        if args.single_launch:
+            print("launched %s" % name, flush=True)
+            continue
         row.update({"ms": seconds * 1e3, "decompressed_gbs": out_bytes / seconds / 1e9, "algorithmic_gbs": algorithmic / seconds / 1e9,
                     "frac_of_measured_peak": algorithmic / seconds / 1e9 / peak, "bit_exact": correct})
         if reference is not None and case.ref_ok:
