@@ -22,6 +22,14 @@
 #define GIDDY_SEGMENT_WARPS_PER_BLOCK 8
 #define GIDDY_BITMAPS_CONTAINERS_PER_TILE 32
 
+/* DZB-variable: a warp decodes a segment in tiles of this many elements, staging each tile's bytes,
+ * per-vector byte offsets and size fields in this much dynamic shared memory per warp (U = uncompressed
+ * element bytes): data (tile x U + 64), offsets (2 bytes per 16-byte output vector), size fields (tile x 4
+ * bits), one mbarrier; rounded up to a multiple of 128. */
+#define GIDDY_DZBV_TILE_ELEMENTS 1024
+#define GIDDY_DZBV_SHARED_BYTES_PER_WARP(U) \
+	((((GIDDY_DZBV_TILE_ELEMENTS * (U) + 64) + (2 * GIDDY_DZBV_TILE_ELEMENTS * (U) / 16) + (GIDDY_DZBV_TILE_ELEMENTS / 2) + 16) + 127) / 128 * 128)
+
 /* Patching kernels */
 #define GIDDY_SCATTER_UNROLL 8
 #define GIDDY_SCATTER_BLOCK_THREADS 256

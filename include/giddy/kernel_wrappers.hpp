@@ -743,6 +743,8 @@ public:
 	{
 		if (segment_length == 0) { throw ::std::invalid_argument("The segment length must be a positive number"); }
 		detail::configure_warp_per_unit(*this, util::div_rounding_up(length_in_elements, segment_length), GIDDY_SEGMENT_WARPS_PER_BLOCK);
+		// each warp stages tiles of its segment (bytes via TMA, offsets, size fields) in shared memory
+		dynamic_shared_memory_requirement.per_length_unit = GIDDY_DZBV_SHARED_BYTES_PER_WARP(UncompressedSize) / warp_size;
 	}
 };
 

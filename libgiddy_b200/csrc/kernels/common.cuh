@@ -162,6 +162,62 @@ __device__ __forceinline__ void store_pack_16(void* p, const byte_pack<16>& v)
 	store_streaming_16(p, make_uint4(v.u32[0], v.u32[1], v.u32[2], v.u32[3]));
 }
 
+// ---- TMA bulk copies (global -> shared) completing on an mbarrier -------------------------------
+// One thread arms the barrier with the byte count and issues the copy (SASS: UBLKCP); every thread
+// that will read the staged bytes waits for the barrier's phase to flip.  Source, destination and size
+// must be multiples of 16 bytes.
+
+__device__ __forceinline__ uint32_t shared_address(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbarrier_init(uint64_t* barrier, unsigned arrivals)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(shared_address(barrier)), "r"(arrivals) : "memory");
+	// make the initialised barrier visible to the async (TMA) proxy
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbarrier_expect_bytes(uint64_t* barrier, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(shared_address(barrier)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbarrier_arrive(uint64_t* barrier)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(shared_address(barrier)) : "memory");
+}
+
+__device__ __forceinline__ void mbarrier_wait(uint64_t* barrier, uint32_t phase_parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_LOOP:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra WAIT_DONE;\n"
+		"bra WAIT_LOOP;\n"
+		"WAIT_DONE:\n"
+		"}\n" :: "r"(shared_address(barrier)), "r"(phase_parity) : "memory");
+}
+
+// Order this thread's earlier generic-proxy accesses to shared memory before later async-proxy (TMA) ones.
+__device__ __forceinline__ void fence_proxy_async_shared()
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void tma_bulk_load(void* shared_destination, const void* global_source, uint32_t bytes, uint64_t* barrier)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(shared_address(shared_destination)), "l"(global_source), "r"(bytes), "r"(shared_address(barrier)) : "memory");
+}
+
+__device__ __forceinline__ uint32_t dynamic_shared_memory_size()
+{
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(r));
+	return r;
+}
+
 // ---- warp-level scans ------------------------------------------------------------------------
 
 template <typename T>

@@ -3,16 +3,31 @@
 // 32- or 64-bit containers, and every segment has the byte offset of its first element as
 // an anchor.
 //
-// One warp decodes one anchored segment, a "row" of 32 lanes x E elements at a time (E = 16 /
-// sizeof(Uncompressed): one 16-byte output vector per lane, 512 contiguous bytes per warp
-// store).  For a row, each lane extracts its E element sizes from the size containers (one
-// container load per lane when the E fields share a container), the lane totals go through
-// one warp-shuffle exclusive scan to give every lane its byte offset, and each element is
-// assembled from the (at most three) aligned 32-bit words which hold its bytes with a funnel
-// shift -- no byte-granular loads, no local-memory staging (the reference memcpy's byte by
-// byte, src/kernels/decompression/discard_zero_bytes_variable.cuh:196-213).  The byte stream
-// of a row is contiguous, so neighbouring lanes read neighbouring words and the stream is
-// fetched from HBM once and then served by L1.  Several rows are in flight per warp.
+// One warp decodes one anchored segment, in tiles of 1024 elements.  Two paths:
+//
+// * staged (the common shapes: 1, 2 or 4 bits per size field, segments which begin on a 32-bit
+//   word of the size-field stream): per tile the warp
+//     1. reads the tile's size fields with one coalesced access per lane (a lane owns 32
+//        consecutive elements), sums them with population counts, and a single warp-shuffle scan
+//        gives every lane its byte offset and the warp the tile's byte count;
+//     2. stages the tile's bytes in shared memory with ONE TMA bulk copy (cp.async.bulk, SASS
+//        UBLKCP) completing on a per-warp mbarrier -- the 16-byte-aligned body of the byte range;
+//        the < 16 trailing bytes are fetched by four lanes, so nothing past the stream's last
+//        word is ever read.  When the tile is a whole segment its byte range is known from the
+//        next anchor and the copy is issued before the size fields have even arrived;
+//     3. writes the byte offset of every 16-byte output vector (2 bytes each) and the size words
+//        to shared memory, and
+//     4. expands: 32 lanes x E elements per row (E = 16 / sizeof(Uncompressed)); a lane looks up
+//        its vector's offset and size fields, assembles each element from the two or three
+//        aligned shared-memory words holding its bytes with a funnel shift, and the warp stores
+//        512 contiguous bytes.
+//   The compressed bytes are read from HBM exactly once, no global access is narrower than
+//   a sector, and there is no data-dependent loop.
+// * generic (any field width, any alignment, or a launch without the shared memory): rows of
+//   32 lanes x E elements; sizes straight from the containers, one warp scan per row, elements
+//   assembled from aligned global words served by L1.
+// (The reference walks a segment with one warp, 32 elements per iteration, memcpy'ing byte by
+// byte through local memory: src/kernels/decompression/discard_zero_bytes_variable.cuh:196-213,276-310.)
 #pragma once
 #ifndef GIDDY_B200_KERNELS_DZB_VARIABLE_CUH_
 #define GIDDY_B200_KERNELS_DZB_VARIABLE_CUH_
@@ -151,6 +166,199 @@ __device__ __forceinline__ void decode_segment(
 	}
 }
 
+// ---- the staged path ----------------------------------------------------------------------------------
+
+constexpr unsigned tile_elements = GIDDY_DZBV_TILE_ELEMENTS;
+constexpr unsigned elements_per_lane = tile_elements / warp_size; // 32: a lane's size fields fill `bits` 32-bit words
+static_assert(elements_per_lane == 32, "a lane owns 32 consecutive elements of a tile");
+constexpr unsigned max_staged_bits = 4;
+
+template <unsigned U> constexpr unsigned shared_memory_bytes_per_warp() { return GIDDY_DZBV_SHARED_BYTES_PER_WARP(U); }
+
+template <unsigned U>
+struct tile_storage {
+	static constexpr unsigned E = 16 / U;
+	static constexpr unsigned data_bytes = tile_elements * U + 64;
+	static constexpr unsigned num_vectors = tile_elements / E;
+	uint8_t*  data;     // [data_bytes]   the tile's bytes; the first one is at data[head]
+	uint16_t* offsets;  // [num_vectors]  byte offset, within the tile, of each output vector's first element
+	uint32_t* fields;   // [tile_elements * bits / 32] the tile's size fields, a flat little-endian bit stream
+	uint64_t* barrier;
+
+	__device__ __forceinline__ explicit tile_storage(unsigned char* warp_memory) :
+		data(warp_memory),
+		offsets(reinterpret_cast<uint16_t*>(warp_memory + data_bytes)),
+		fields(reinterpret_cast<uint32_t*>(warp_memory + data_bytes + 2 * num_vectors)),
+		barrier(reinterpret_cast<uint64_t*>(warp_memory + data_bytes + 2 * num_vectors + tile_elements * max_staged_bits / 8)) { }
+};
+
+// Sum of the `bits`-wide fields of x (bits in {1, 2, 4}).
+template <unsigned bits>
+__device__ __forceinline__ unsigned sum_of_fields(uint32_t x)
+{
+	if (bits == 1) { return __popc(x); }
+	if (bits == 2) { return __popc(x & 0x55555555u) + 2 * __popc(x & 0xAAAAAAAAu); }
+	return __popc(x & 0x11111111u) + 2 * __popc(x & 0x22222222u) + 4 * __popc(x & 0x44444444u) + 8 * __popc(x & 0x88888888u);
+}
+
+// The `size` low bytes at shared-memory byte offset `at`, zero-extended.
+template <unsigned U>
+__device__ __forceinline__ uint_t<U> assemble_from_shared(const uint8_t* data, unsigned at, unsigned size)
+{
+	const uint32_t* words = reinterpret_cast<const uint32_t*>(data + (at & ~3u));
+	const unsigned shift = (at & 3u) * 8;
+	const uint32_t w0 = words[0], w1 = words[1];
+	if (U <= 4) {
+		uint32_t v = __funnelshift_r(w0, w1, shift);
+		v &= (size >= 4) ? 0xffffffffu : ((1u << (8 * size)) - 1u);
+		return (uint_t<U>) v;
+	}
+	const uint32_t w2 = words[2];
+	uint64_t v = (uint64_t) __funnelshift_r(w0, w1, shift) | ((uint64_t) __funnelshift_r(w1, w2, shift) << 32);
+	v &= (size >= 8) ? ~(uint64_t) 0 : (((uint64_t) 1 << (8 * size)) - 1u);
+	return (uint_t<U>) v;
+}
+
+// Decode one segment, tile by tile.  Requires: bits in {1, 2, 4}; (first_element * bits) % 32 == 0;
+// `out` 16-byte aligned; packed sizes readable as 32-bit words up to num_field_words.
+template <unsigned U, unsigned bits, typename Offset>
+__device__ __forceinline__ void decode_segment_staged(
+	uint_t<U>*        __restrict__  out,              // the segment's first output element
+	const uint8_t*    __restrict__  compressed_data,
+	uint64_t                        segment_first_byte,
+	bool                            next_anchor_known,
+	uint64_t                        next_anchor,
+	const uint32_t*   __restrict__  field_words,      // the packed size fields as a stream of 32-bit words
+	uint64_t                        num_field_words,
+	uint64_t                        first_element,    // global index of the segment's first element
+	uint64_t                        length,
+	unsigned                        min_size,
+	const tile_storage<U>&          tile,
+	uint32_t&                       barrier_phase)
+{
+	constexpr unsigned E = tile_storage<U>::E;
+	constexpr unsigned vectors_per_lane = elements_per_lane / E;
+	const unsigned lane = lane_index();
+	constexpr uint32_t field_mask = (1u << bits) - 1u;
+	uint64_t tile_first_byte = segment_first_byte;
+
+	for (uint64_t tile_start = 0; tile_start < length; tile_start += tile_elements) {
+		const unsigned tile_length = (unsigned) minimum<uint64_t>(tile_elements, length - tile_start);
+		const bool bytes_known = next_anchor_known && (tile_start + tile_elements >= length);
+
+		// the body of the byte range goes through TMA, its < 16 trailing bytes through four lanes
+		auto stage_bytes = [&](uint64_t past_last_byte) {
+			const uintptr_t first = reinterpret_cast<uintptr_t>(compressed_data) + tile_first_byte;
+			const uintptr_t past_last = reinterpret_cast<uintptr_t>(compressed_data) + past_last_byte;
+			const uintptr_t body_first = first & ~(uintptr_t) 15;
+			const uintptr_t body_past_last = (past_last & ~(uintptr_t) 15) > body_first ? (past_last & ~(uintptr_t) 15) : body_first;
+			const uint32_t body_bytes = (uint32_t)(body_past_last - body_first);
+			if (lane == 0) {
+				fence_proxy_async_shared();
+				if (body_bytes > 0) {
+					mbarrier_expect_bytes(tile.barrier, body_bytes);
+					tma_bulk_load(tile.data, reinterpret_cast<const void*>(body_first), body_bytes, tile.barrier);
+				}
+				else { mbarrier_arrive(tile.barrier); }
+			}
+			// trailing words: [body_past_last, round_up(past_last, 4)), at most 4 of them -- or, when the body is empty,
+			// from the word holding the first byte
+			const uintptr_t tail_first = (body_bytes > 0) ? body_past_last : (first & ~(uintptr_t) 3);
+			const uintptr_t tail_word = tail_first + 4 * lane;
+			if (lane < 8 && tail_word < past_last) {
+				*reinterpret_cast<uint32_t*>(tile.data + (tail_word - body_first)) = __ldg(reinterpret_cast<const uint32_t*>(tail_word));
+			}
+		};
+		if (bytes_known) { stage_bytes(next_anchor); }
+
+		// 1. this lane's 32 size fields: `bits` consecutive words of the field stream
+		const unsigned lane_elements = (tile_length > lane * elements_per_lane) ?
+			(unsigned) minimum<unsigned>(elements_per_lane, tile_length - lane * elements_per_lane) : 0u;
+		const uint64_t lane_first_word = ((first_element + tile_start) * bits) / 32 + (uint64_t) lane * bits;
+		uint32_t words[bits];
+		#pragma unroll
+		for (unsigned k = 0; k < bits; k++) {
+			words[k] = (lane_first_word + k < num_field_words) ? load_streaming_4(field_words + lane_first_word + k) : 0u;
+		}
+		// fields of elements past the tile's end do not count
+		unsigned lane_bytes = lane_elements * min_size;
+		{
+			const unsigned valid_bits = lane_elements * bits;
+			#pragma unroll
+			for (unsigned k = 0; k < bits; k++) {
+				const unsigned bits_here = (valid_bits > 32 * k) ? minimum<unsigned>(32u, valid_bits - 32 * k) : 0u;
+				const uint32_t keep = (bits_here >= 32) ? 0xffffffffu : ((1u << bits_here) - 1u);
+				words[k] &= keep;
+				lane_bytes += sum_of_fields<bits>(words[k]);
+			}
+		}
+		const unsigned inclusive = warp_inclusive_sum(lane_bytes);
+		const unsigned tile_bytes = __shfl_sync(full_mask, inclusive, warp_size - 1);
+		if (!bytes_known) { stage_bytes(tile_first_byte + tile_bytes); }
+
+		// 2. per-vector byte offsets and the size words, to shared memory
+		{
+			unsigned running = inclusive - lane_bytes;
+			constexpr unsigned fields_per_pack = (vectors_per_lane >= 2) ? 2 : 1;
+			#pragma unroll
+			for (unsigned v = 0; v < vectors_per_lane; v += fields_per_pack) {
+				uint32_t packed = 0;
+				#pragma unroll
+				for (unsigned h = 0; h < fields_per_pack; h++) {
+					packed |= (running & 0xffffu) << (16 * h);
+					// add the sizes of this vector's E elements
+					constexpr unsigned fields_mask = (E * bits >= 32) ? 0xffffffffu : ((1u << ((E * bits) % 32)) - 1u);
+					const unsigned first_bit = (v + h) * E * bits; // a compile-time constant once unrolled; < 32 * bits
+					const uint32_t chunk = (words[first_bit / 32] >> (first_bit % 32)) & fields_mask;
+					const unsigned elements_before = (v + h) * E;
+					const unsigned elements_here = (lane_elements > elements_before) ? minimum<unsigned>(E, lane_elements - elements_before) : 0u;
+					running += sum_of_fields<bits>(chunk) + elements_here * min_size;
+				}
+				if (fields_per_pack == 2) { reinterpret_cast<uint32_t*>(tile.offsets)[(lane * vectors_per_lane + v) / 2] = packed; }
+				else { tile.offsets[lane * vectors_per_lane + v] = (uint16_t) packed; }
+			}
+			#pragma unroll
+			for (unsigned k = 0; k < bits; k++) { tile.fields[lane * bits + k] = words[k]; }
+		}
+		__syncwarp();
+		mbarrier_wait(tile.barrier, barrier_phase);
+		barrier_phase ^= 1u;
+
+		// 3. expand
+		const unsigned head = (unsigned)((reinterpret_cast<uintptr_t>(compressed_data) + tile_first_byte) & 15u);
+		const uint8_t* const bytes = tile.data; // 16-byte aligned; the tile's first byte is bytes[head]
+		uint_t<U>* const tile_out = out + tile_start;
+		const unsigned num_rows = (tile_length + warp_size * E - 1) / (warp_size * E);
+		for (unsigned row = 0; row < num_rows; row++) {
+			const unsigned vector = row * warp_size + lane;
+			const unsigned p = vector * E;
+			if (p >= tile_length) { break; }
+			unsigned at = head + tile.offsets[vector];
+			const unsigned first_bit = p * bits;
+			uint32_t chunk = tile.fields[first_bit / 32] >> (first_bit % 32);
+			uint_t<U> elements[E];
+			#pragma unroll
+			for (unsigned j = 0; j < E; j++) {
+				const unsigned size = ((chunk >> (j * bits)) & field_mask) + min_size;
+				elements[j] = (p + j < tile_length) ? assemble_from_shared<U>(bytes, at, size) : (uint_t<U>) 0;
+				at += size;
+			}
+			if (p + E <= tile_length) {
+				byte_pack<16> vec;
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) { vec.template set<U>(j, elements[j]); }
+				store_pack_16(tile_out + p, vec);
+			}
+			else {
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) { if (p + j < tile_length) { tile_out[p + j] = elements[j]; } }
+			}
+		}
+		__syncwarp(); // the tile's shared memory is free again
+		tile_first_byte += tile_bytes;
+	}
+}
+
 } // namespace dzbv_detail
 
 // -------------------------------------------------------------------------------------------------
@@ -161,7 +369,7 @@ __device__ __forceinline__ void decode_segment(
 //   decompressed[i] = those bytes, zero-extended (little-endian).
 // -------------------------------------------------------------------------------------------------
 template <unsigned IndexSize, unsigned U, unsigned ElementSizesContainerSize>
-__global__ void discard_zero_bytes_variable_decompress(
+__global__ void __launch_bounds__(GIDDY_SEGMENT_WARPS_PER_BLOCK * 32, 4) discard_zero_bytes_variable_decompress(
 	uint_t<U>*                                __restrict__  decompressed,
 	const uint8_t*                            __restrict__  compressed_data,
 	const uint_t<ElementSizesContainerSize>*  __restrict__  packed_element_sizes,
@@ -174,19 +382,59 @@ __global__ void discard_zero_bytes_variable_decompress(
 	constexpr unsigned CS = ElementSizesContainerSize;
 	constexpr unsigned E = 16 / U;
 	using offset_t = size_type<IndexSize>;
-	const dzbv_detail::size_field_locator<CS> locator(bits_per_element_size, min_represented_element_size);
+	using namespace dzbv_detail;
 	const uint64_t num_segments = ((uint64_t) length + segment_length - 1) / segment_length;
 	const bool vectorizable = is_aligned_to(decompressed, 16) && (segment_length % E == 0);
 
+	// The staged path: a flat stream of 1-, 2- or 4-bit fields (no slack bits in a container), every segment beginning on
+	// a 32-bit word of it, E fields never straddling a word, and the shared memory to stage tiles in.
+	const unsigned bits = bits_per_element_size;
+	const bool staged = vectorizable && (bits == 1 || bits == 2 || bits == 4) && (E * bits <= 32) &&
+		(((uint64_t) segment_length * bits) % 32 == 0) &&
+		(dynamic_shared_memory_size() >= warps_per_block() * shared_memory_bytes_per_warp<U>());
+
+	if (staged) {
+		const tile_storage<U> tile(warp_shared_memory(shared_memory_bytes_per_warp<U>()));
+		if (lane_index() == 0) { mbarrier_init(tile.barrier, 1); }
+		__syncwarp();
+		uint32_t barrier_phase = 0;
+		const uint32_t* field_words = reinterpret_cast<const uint32_t*>(packed_element_sizes);
+		const uint64_t sizes_per_container = (8 * CS) / bits;
+		const uint64_t num_field_words = (((uint64_t) length + sizes_per_container - 1) / sizes_per_container) * (CS / 4);
+		for (uint64_t segment = global_warp_index(); segment < num_segments; segment += num_warps_in_grid()) {
+			const uint64_t start = segment * segment_length;
+			const uint64_t this_length = minimum<uint64_t>(segment_length, length - start);
+			const uint64_t first_byte = __ldg(position_anchors + segment);
+			const bool next_anchor_known = segment + 1 < num_segments;
+			const uint64_t next_anchor = next_anchor_known ? (uint64_t) __ldg(position_anchors + segment + 1) : 0;
+			switch (bits) {
+			case 1:
+				decode_segment_staged<U, 1, offset_t>(decompressed + start, compressed_data, first_byte, next_anchor_known, next_anchor,
+					field_words, num_field_words, start, this_length, min_represented_element_size, tile, barrier_phase);
+				break;
+			case 2:
+				decode_segment_staged<U, 2, offset_t>(decompressed + start, compressed_data, first_byte, next_anchor_known, next_anchor,
+					field_words, num_field_words, start, this_length, min_represented_element_size, tile, barrier_phase);
+				break;
+			default:
+				decode_segment_staged<U, (E * 4 <= 32 ? 4 : 2), offset_t>(decompressed + start, compressed_data, first_byte, next_anchor_known, next_anchor,
+					field_words, num_field_words, start, this_length, min_represented_element_size, tile, barrier_phase);
+				break;
+			}
+		}
+		return;
+	}
+
+	const size_field_locator<CS> locator(bits_per_element_size, min_represented_element_size);
 	for (uint64_t segment = global_warp_index(); segment < num_segments; segment += num_warps_in_grid()) {
 		const uint64_t start = segment * segment_length;
 		const uint64_t this_length = minimum<uint64_t>(segment_length, length - start);
 		const uint8_t* segment_bytes = compressed_data + __ldg(position_anchors + segment);
 		if (vectorizable) {
-			dzbv_detail::decode_segment<U, CS, E, offset_t>(decompressed + start, segment_bytes, packed_element_sizes, start, this_length, locator);
+			decode_segment<U, CS, E, offset_t>(decompressed + start, segment_bytes, packed_element_sizes, start, this_length, locator);
 		}
 		else {
-			dzbv_detail::decode_segment<U, CS, 1, offset_t>(decompressed + start, segment_bytes, packed_element_sizes, start, this_length, locator);
+			decode_segment<U, CS, 1, offset_t>(decompressed + start, segment_bytes, packed_element_sizes, start, this_length, locator);
 		}
 	}
 }

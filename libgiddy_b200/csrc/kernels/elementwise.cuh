@@ -117,6 +117,7 @@ __global__ void frame_of_reference_decompress(
 	const uint64_t num_vectors = length / E;
 	const uint64_t vectors_per_tile = (uint64_t) blockDim.x * unroll;
 
+	#pragma unroll 1
 	for (uint64_t tile_start = (uint64_t) blockIdx.x * vectors_per_tile; tile_start < num_vectors;
 	     tile_start += (uint64_t) gridDim.x * vectors_per_tile)
 	{
@@ -179,6 +180,7 @@ __global__ void model_decompress(
 	}
 	const uint64_t num_vectors = length / E;
 	const uint64_t vectors_per_tile = (uint64_t) blockDim.x * unroll;
+	#pragma unroll 1
 	for (uint64_t tile_start = (uint64_t) blockIdx.x * vectors_per_tile; tile_start < num_vectors;
 	     tile_start += (uint64_t) gridDim.x * vectors_per_tile)
 	{
@@ -225,6 +227,7 @@ __global__ void discard_zero_bytes_fixed_decompress(
 	}
 	const uint64_t num_vectors = length / E;
 	const uint64_t vectors_per_tile = (uint64_t) blockDim.x * unroll;
+	#pragma unroll 1
 	for (uint64_t tile_start = (uint64_t) blockIdx.x * vectors_per_tile; tile_start < num_vectors;
 	     tile_start += (uint64_t) gridDim.x * vectors_per_tile)
 	{
@@ -292,6 +295,7 @@ __global__ void dictionary_decompress(
 	}
 	const uint64_t num_vectors = length / E;
 	const uint64_t vectors_per_tile = (uint64_t) blockDim.x * unroll;
+	#pragma unroll 1
 	for (uint64_t tile_start = (uint64_t) blockIdx.x * vectors_per_tile; tile_start < num_vectors;
 	     tile_start += (uint64_t) gridDim.x * vectors_per_tile)
 	{

@@ -204,7 +204,7 @@ def dzbf_case(seed, n, U, C, I=4):
     return Case("dzbf-I%d-U%d-C%d-n%d" % (I, U, C, n), "discard_zero_bytes_fixed", {"compressed_input": compressed}, dict(n=n), expected, launch)
 
 
-def dzbv_case(seed, n, L, U, CS, bits, min_size, I=4):
+def dzbv_case(seed, n, L, U, CS, bits, min_size, I=4, ref_ok=None):
     r = rng(8, seed, n, L, U, CS, bits)
     max_size = min(U, min_size + (1 << bits) - 1)
     widths = r.integers(min_size, max_size + 1, n)
@@ -224,7 +224,7 @@ def dzbv_case(seed, n, L, U, CS, bits, min_size, I=4):
         S.discard_zero_bytes_variable(out, t["compressed_data"], t["packed_element_sizes"], t["position_anchors"], L, n, min_size, bits,
                                       uncompressed_size=U, container_size=CS, index_size=I, library=library, limits=limits)
     return Case("dzbv-I%d-U%d-CS%d-b%d-m%d-n%d-L%d" % (I, U, CS, bits, min_size, n, L), "discard_zero_bytes_variable", enc, dict(n=n, L=L),
-                expected, launch, ref_ok=(n % L == 0))
+                expected, launch, ref_ok=(n % L == 0) if ref_ok is None else ref_ok)
 
 
 def bitmaps_case(seed, n, U, K, use_dictionary=True, I=4, alignment=2):
@@ -354,6 +354,16 @@ def all_cases():
     cases.append(dzbv_case(3, 40000, 1024, 4, 4, 3, 0))                   # 3-bit fields (10 per container), zero-size elements
     cases.append(dzbv_case(4, 40000, 1024, 8, 8, 4, 0))
     cases.append(dzbv_case(5, 1 << 20, 1024, 4, 4, 2, 1))
+    # the staged (TMA) path's corners: several tiles per segment, partial tiles, ragged tails, tiny segments, zero-size elements
+    cases.append(dzbv_case(6, 5 * 4096, 4096, 4, 4, 2, 1))
+    cases.append(dzbv_case(7, 3 * 2048 + 1040, 2048, 8, 8, 4, 0, ref_ok=False))
+    cases.append(dzbv_case(8, 50000 + 3, 1008, 4, 4, 2, 1, ref_ok=False))
+    cases.append(dzbv_case(9, 40000 + 7, 1040, 4, 8, 2, 0, ref_ok=False))
+    cases.append(dzbv_case(10, 4000, 16, 4, 4, 2, 1, ref_ok=False))
+    cases.append(dzbv_case(11, 70000, 3000 * 16, 2, 4, 1, 1, ref_ok=False))
+    cases.append(dzbv_case(12, 33000, 1024, 4, 4, 4, 0, ref_ok=False))
+    cases.append(dzbv_case(13, 64 * 1024, 1024, 8, 4, 2, 5, ref_ok=False))
+    cases.append(dzbv_case(14, 20, 1024, 4, 4, 2, 1, ref_ok=False))
     # Incidence bitmaps (5 keys)
     for (U, use_dictionary) in [(1, True), (2, True), (4, True), (8, True), (1, False)]:
         cases.append(bitmaps_case(0, 64 * 1024, U, 16, use_dictionary))
