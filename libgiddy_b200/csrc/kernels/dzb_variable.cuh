@@ -201,22 +201,75 @@ __device__ __forceinline__ unsigned sum_of_fields(uint32_t x)
 	return __popc(x & 0x11111111u) + 2 * __popc(x & 0x22222222u) + 4 * __popc(x & 0x44444444u) + 8 * __popc(x & 0x88888888u);
 }
 
-// The `size` low bytes at shared-memory byte offset `at`, zero-extended.
-template <unsigned U>
-__device__ __forceinline__ uint_t<U> assemble_from_shared(const uint8_t* data, unsigned at, unsigned size)
+// x << s, with s clamped to 32 (so that s == 32 gives 0, as PTX's shl does)
+__device__ __forceinline__ uint32_t shift_left_clamped(uint32_t x, unsigned s)
 {
-	const uint32_t* words = reinterpret_cast<const uint32_t*>(data + (at & ~3u));
-	const unsigned shift = (at & 3u) * 8;
-	const uint32_t w0 = words[0], w1 = words[1];
-	if (U <= 4) {
-		uint32_t v = __funnelshift_r(w0, w1, shift);
-		v &= (size >= 4) ? 0xffffffffu : ((1u << (8 * size)) - 1u);
-		return (uint_t<U>) v;
+	uint32_t r;
+	asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
+	return r;
+}
+
+// Sums of the fields within each byte of x, for fields of `bits` bits (bits in {1, 2, 4}).
+template <unsigned bits>
+__device__ __forceinline__ uint32_t field_sums_per_byte(uint32_t x)
+{
+	if (bits == 1) {
+		x = x - ((x >> 1) & 0x55555555u);
+		x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+		return (x + (x >> 4)) & 0x0F0F0F0Fu;
 	}
-	const uint32_t w2 = words[2];
-	uint64_t v = (uint64_t) __funnelshift_r(w0, w1, shift) | ((uint64_t) __funnelshift_r(w1, w2, shift) << 32);
-	v &= (size >= 8) ? ~(uint64_t) 0 : (((uint64_t) 1 << (8 * size)) - 1u);
-	return (uint_t<U>) v;
+	if (bits == 2) {
+		x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+		return (x + (x >> 4)) & 0x0F0F0F0Fu;
+	}
+	return (x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu);
+}
+
+// One 16-byte output vector: E elements whose bytes lie back to back in shared memory from byte
+// offset `at` of `data` (16-byte aligned), their size fields in the low E * bits bits of `chunk`.
+// The (at most) 16 bytes are read as five aligned words and funnel-shifted into a 4-word window
+// which begins at the first element's first byte; each element is the window's low bytes under a
+// mask, after which the window is shifted right by the element's size.
+template <unsigned U, unsigned bits>
+__device__ __forceinline__ byte_pack<16> assemble_vector(const uint8_t* data, unsigned at, uint32_t chunk, unsigned min_size)
+{
+	constexpr unsigned E = 16 / U;
+	constexpr uint32_t field_mask = (1u << bits) - 1u;
+	const uint32_t* aligned = reinterpret_cast<const uint32_t*>(data + (at & ~3u));
+	const uint32_t w0 = aligned[0], w1 = aligned[1], w2 = aligned[2], w3 = aligned[3], w4 = aligned[4];
+	const unsigned shift = at * 8; // funnel shifts in wrap mode use the low 5 bits: (at % 4) * 8
+	uint32_t window[5] = { __funnelshift_r(w0, w1, shift), __funnelshift_r(w1, w2, shift), __funnelshift_r(w2, w3, shift),
+		__funnelshift_r(w3, w4, shift), 0u };
+	byte_pack<16> vec;
+	#pragma unroll
+	for (unsigned j = 0; j < E; j++) {
+		const unsigned size_in_bits = (((chunk >> (j * bits)) & field_mask) + min_size) * 8;
+		// how many window words the elements after this one may still need
+		const unsigned words_after = ((E - 1 - j) * U + 3) / 4; // (a compile-time constant once unrolled)
+		if (U <= 4) {
+			vec.template set<U>(j, (uint_t<U>)(window[0] & ~shift_left_clamped(0xffffffffu, size_in_bits)));
+			#pragma unroll
+			for (unsigned k = 0; k < 4; k++) {
+				if (k < words_after) { window[k] = __funnelshift_rc(window[k], window[k + 1], size_in_bits); }
+			}
+		}
+		else {
+			const unsigned high_bits = (size_in_bits > 32 ? size_in_bits : 32u) - 32u;
+			const uint32_t lo = window[0] & ~shift_left_clamped(0xffffffffu, size_in_bits);
+			const uint32_t hi = window[1] & ~shift_left_clamped(0xffffffffu, high_bits);
+			vec.template set<U>(j, (uint_t<U>)((uint64_t) lo | ((uint64_t) hi << 32)));
+			const unsigned low_bits = size_in_bits - high_bits; // <= 32
+			#pragma unroll
+			for (unsigned k = 0; k < 4; k++) { // (one word more than needed: the second shift pulls it in)
+				if (k < words_after + 1) { window[k] = __funnelshift_rc(window[k], window[k + 1], low_bits); }
+			}
+			#pragma unroll
+			for (unsigned k = 0; k < 4; k++) {
+				if (k < words_after) { window[k] = __funnelshift_rc(window[k], window[k + 1], high_bits); }
+			}
+		}
+	}
+	return vec;
 }
 
 // Decode one segment, tile by tile.  Requires: bits in {1, 2, 4}; (first_element * bits) % 32 == 0;
@@ -297,7 +350,21 @@ __device__ __forceinline__ void decode_segment_staged(
 		if (!bytes_known) { stage_bytes(tile_first_byte + tile_bytes); }
 
 		// 2. per-vector byte offsets and the size words, to shared memory
-		{
+		if (E * bits == 8 && lane_elements == elements_per_lane) {
+			// a vector's fields fill a byte of a field word: byte-wise sums, then a multiply gives the prefix sums
+			unsigned running = inclusive - lane_bytes;
+			#pragma unroll
+			for (unsigned k = 0; k < bits; k++) {
+				const uint32_t sums = field_sums_per_byte<bits>(words[k]) + (E * min_size) * 0x01010101u; // bytes of the 4 vectors
+				const uint32_t before = sums * 0x01010100u;                // byte v: bytes of the vectors before vector v
+				const uint32_t base = running * 0x00010001u;
+				const uint32_t offsets01 = __byte_perm(before, 0u, 0x4140) + base;
+				const uint32_t offsets23 = __byte_perm(before, 0u, 0x4342) + base;
+				reinterpret_cast<uint2*>(tile.offsets)[lane * bits + k] = make_uint2(offsets01, offsets23);
+				running += (sums * 0x01010101u) >> 24;
+			}
+		}
+		else {
 			unsigned running = inclusive - lane_bytes;
 			constexpr unsigned fields_per_pack = (vectors_per_lane >= 2) ? 2 : 1;
 			#pragma unroll
@@ -317,9 +384,9 @@ __device__ __forceinline__ void decode_segment_staged(
 				if (fields_per_pack == 2) { reinterpret_cast<uint32_t*>(tile.offsets)[(lane * vectors_per_lane + v) / 2] = packed; }
 				else { tile.offsets[lane * vectors_per_lane + v] = (uint16_t) packed; }
 			}
-			#pragma unroll
-			for (unsigned k = 0; k < bits; k++) { tile.fields[lane * bits + k] = words[k]; }
 		}
+		#pragma unroll
+		for (unsigned k = 0; k < bits; k++) { tile.fields[lane * bits + k] = words[k]; }
 		__syncwarp();
 		mbarrier_wait(tile.barrier, barrier_phase);
 		barrier_phase ^= 1u;
@@ -328,30 +395,34 @@ __device__ __forceinline__ void decode_segment_staged(
 		const unsigned head = (unsigned)((reinterpret_cast<uintptr_t>(compressed_data) + tile_first_byte) & 15u);
 		const uint8_t* const bytes = tile.data; // 16-byte aligned; the tile's first byte is bytes[head]
 		uint_t<U>* const tile_out = out + tile_start;
-		const unsigned num_rows = (tile_length + warp_size * E - 1) / (warp_size * E);
-		for (unsigned row = 0; row < num_rows; row++) {
-			const unsigned vector = row * warp_size + lane;
-			const unsigned p = vector * E;
-			if (p >= tile_length) { break; }
-			unsigned at = head + tile.offsets[vector];
-			const unsigned first_bit = p * bits;
-			uint32_t chunk = tile.fields[first_bit / 32] >> (first_bit % 32);
-			uint_t<U> elements[E];
+		if (tile_length == tile_elements) { // a full tile: every offset below is an immediate
+			constexpr unsigned words_per_row = warp_size * E * bits / 32;
+			const uint16_t* lane_offsets = tile.offsets + lane;
+			const uint32_t* lane_fields = tile.fields + (lane * E * bits) / 32;
+			const unsigned field_shift = (lane * E * bits) % 32;
+			uint_t<U>* lane_out = tile_out + lane * E;
 			#pragma unroll
-			for (unsigned j = 0; j < E; j++) {
-				const unsigned size = ((chunk >> (j * bits)) & field_mask) + min_size;
-				elements[j] = (p + j < tile_length) ? assemble_from_shared<U>(bytes, at, size) : (uint_t<U>) 0;
-				at += size;
+			for (unsigned row = 0; row < tile_elements / (warp_size * E); row++) {
+				const unsigned at = head + lane_offsets[row * warp_size];
+				const uint32_t chunk = lane_fields[row * words_per_row] >> field_shift;
+				store_pack_16(lane_out + row * warp_size * E, assemble_vector<U, bits>(bytes, at, chunk, min_size));
 			}
-			if (p + E <= tile_length) {
-				byte_pack<16> vec;
-				#pragma unroll
-				for (unsigned j = 0; j < E; j++) { vec.template set<U>(j, elements[j]); }
-				store_pack_16(tile_out + p, vec);
-			}
-			else {
-				#pragma unroll
-				for (unsigned j = 0; j < E; j++) { if (p + j < tile_length) { tile_out[p + j] = elements[j]; } }
+		}
+		else {
+			const unsigned num_rows = (tile_length + warp_size * E - 1) / (warp_size * E);
+			for (unsigned row = 0; row < num_rows; row++) {
+				const unsigned vector = row * warp_size + lane;
+				const unsigned p = vector * E;
+				if (p >= tile_length) { break; }
+				const unsigned at = head + tile.offsets[vector];
+				const unsigned first_bit = p * bits;
+				const uint32_t chunk = tile.fields[first_bit / 32] >> (first_bit % 32);
+				const byte_pack<16> vec = assemble_vector<U, bits>(bytes, at, chunk, min_size);
+				if (p + E <= tile_length) { store_pack_16(tile_out + p, vec); }
+				else {
+					#pragma unroll
+					for (unsigned j = 0; j < E; j++) { if (p + j < tile_length) { tile_out[p + j] = vec.template get<U>(j); } }
+				}
 			}
 		}
 		__syncwarp(); // the tile's shared memory is free again
