@@ -39,6 +39,10 @@ namespace kernels {
 
 using namespace giddy::device;
 
+#ifndef GIDDY_DZBV_MIN_BLOCKS
+#define GIDDY_DZBV_MIN_BLOCKS 5
+#endif
+
 namespace dzbv_detail {
 
 // Where the size field of an element lives; reference get_element_size,
@@ -322,9 +326,8 @@ __device__ __forceinline__ void decode_segment_staged(
 				*reinterpret_cast<uint32_t*>(tile.data + (tail_word - body_first)) = __ldg(reinterpret_cast<const uint32_t*>(tail_word));
 			}
 		};
-		if (bytes_known) { stage_bytes(next_anchor); }
-
-		// 1. this lane's 32 size fields: `bits` consecutive words of the field stream
+		// 1. this lane's 32 size fields: `bits` consecutive words of the field stream (requested before the byte range's
+		// anchors are consumed, so that the two round trips overlap)
 		const unsigned lane_elements = (tile_length > lane * elements_per_lane) ?
 			(unsigned) minimum<unsigned>(elements_per_lane, tile_length - lane * elements_per_lane) : 0u;
 		const uint64_t lane_first_word = ((first_element + tile_start) * bits) / 32 + (uint64_t) lane * bits;
@@ -333,6 +336,7 @@ __device__ __forceinline__ void decode_segment_staged(
 		for (unsigned k = 0; k < bits; k++) {
 			words[k] = (lane_first_word + k < num_field_words) ? load_streaming_4(field_words + lane_first_word + k) : 0u;
 		}
+		if (bytes_known) { stage_bytes(next_anchor); }
 		// fields of elements past the tile's end do not count
 		unsigned lane_bytes = lane_elements * min_size;
 		{
@@ -440,7 +444,7 @@ __device__ __forceinline__ void decode_segment_staged(
 //   decompressed[i] = those bytes, zero-extended (little-endian).
 // -------------------------------------------------------------------------------------------------
 template <unsigned IndexSize, unsigned U, unsigned ElementSizesContainerSize>
-__global__ void __launch_bounds__(GIDDY_SEGMENT_WARPS_PER_BLOCK * 32, 4) discard_zero_bytes_variable_decompress(
+__global__ void __launch_bounds__(GIDDY_SEGMENT_WARPS_PER_BLOCK * 32, GIDDY_DZBV_MIN_BLOCKS) discard_zero_bytes_variable_decompress(
 	uint_t<U>*                                __restrict__  decompressed,
 	const uint8_t*                            __restrict__  compressed_data,
 	const uint_t<ElementSizesContainerSize>*  __restrict__  packed_element_sizes,
