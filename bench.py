@@ -48,7 +48,9 @@ def parse_args():
     p.add_argument("--impl", default="giddy_b200", choices=["giddy_b200", "reference"])
     p.add_argument("--log2-n", type=int, default=LOG2_N, help="log2 of the number of decompressed elements per GPU")
     p.add_argument("--segment-length", type=int, default=SEGMENT_LENGTH)
-    p.add_argument("--cpu-sample-log2", type=int, default=28, help="log2 of the elements the CPU baseline decodes per pass")
+    p.add_argument("--cpu-sample-log2", type=int, default=30, help="log2 of the elements the CPU baseline decodes per pass")
+    p.add_argument("--cpu-seconds", type=float, default=12.0, help="host time the cpu_baseline leg spends decoding (bounded sample)")
+    p.add_argument("--skip-reference-kernels", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-verify", action="store_true")
@@ -201,16 +203,22 @@ def host_sample(np, log2_elements, segment_length, seed):
             "intra_run_anchor_offsets": (segment_starts - starts[anchors]).astype(np.uint16), "n": n}
 
 
-def time_host_decoder(np, sample, segment_length, passes):
+def time_host_decoder(np, sample, segment_length, passes, seconds=None):
+    """Decode the sample `passes` times -- or, with `seconds`, as many times as fit (at least 3, at most 400)."""
     from oracle import giddy_oracle as O  # the checker / CPU baseline: the only use of oracle/ in this file
     out = np.empty(sample["n"], dtype=np.uint32)
     out[:] = 0  # first touch
     times = []
-    for _ in range(passes):
+    while True:
         t0 = time.perf_counter()
         O.run_length_encoding(sample["run_data"], sample["run_lengths"], sample["position_anchors"],
                               sample["intra_run_anchor_offsets"], segment_length, sample["n"], out=out)
         times.append(time.perf_counter() - t0)
+        if seconds is None:
+            if len(times) >= passes:
+                break
+        elif (len(times) >= 3 and sum(times) >= seconds) or len(times) >= 400:
+            break
     return times, O.num_threads()
 
 
@@ -219,13 +227,13 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = host_sample(np, args.cpu_sample_log2, args.segment_length, 3)
+    sample = host_sample(np, min(args.cpu_sample_log2, args.log2_n), args.segment_length, 3)
     times, threads = time_host_decoder(np, sample, args.segment_length, args.warmup + args.steps)
     timed = times[args.warmup:]
     total = sum(timed)
     value = sample["n"] * 4 * len(timed) / total / 1e9
-    description = "first 2^%d elements of the column (run lengths U{1..31}, L=%d), decoded %d times" % (
-        args.cpu_sample_log2, args.segment_length, len(timed))
+    description = "2^%d elements of the column's distribution (run lengths U{1..31}, L=%d) per step, %d timed steps, %.1f s of host time" % (
+        min(args.cpu_sample_log2, args.log2_n), args.segment_length, len(timed), sum(times))
     print(json.dumps({
         "impl": "reference", "metric": "decompressed GB/s", "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -362,14 +370,20 @@ def run_product_arm(args):
     clocks = sampler.summary(t_begin, t_end) if rank == 0 else None
     sampler.stop()
 
+    reference_kernels = None
+    if rank == 0 and not args.skip_reference_kernels:
+        reference_kernels = time_reference_kernels(args, torch, g, column, out, resolve_arguments, launch_arguments)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         sample = host_sample(np, args.cpu_sample_log2, L, 3)
-        times, threads = time_host_decoder(np, sample, L, 4)
-        best = min(times[1:])
-        cpu_baseline = {"value": sample["n"] * 4 / best / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
-                        "sample": "2^%d elements of the same distribution, best of 3 passes after one warm-up (%.2f s of host time in total)" % (
-                            args.cpu_sample_log2, sum(times))}
+        times, threads = time_host_decoder(np, sample, L, 0, seconds=args.cpu_seconds)
+        timed = times[1:]
+        cpu_baseline = {"value": sample["n"] * 4 * len(timed) / sum(timed) / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+                        "best_pass_value": sample["n"] * 4 / min(timed) / 1e9,
+                        "sample": "2^%d elements of the same distribution (run lengths U{1..31}, L=%d) decoded %d times after one warm-up pass: "
+                                  "%.1f s of host time; scalar C++ host decoder (oracle/giddy_oracle.cpp), OpenMP over segments" % (
+                                      args.cpu_sample_log2, L, len(timed), sum(times))}
 
     if rank == 0:
         print(json.dumps({
@@ -377,11 +391,42 @@ def run_product_arm(args):
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "verified_bit_exact": verified,
+            "reference_kernels": reference_kernels,
             "algorithmic_gbs_all_gpus": algorithmic_total * args.steps / seconds / 1e9,
             "library": library.version(),
         }))
     if distributed:
         dist.destroy_process_group()
+
+
+def time_reference_kernels(args, torch, g, column, out, resolve_arguments, launch_arguments):
+    """A reported baseline, outside the timed region: the reference's OWN kernel and launch-configuration resolver for the
+    same factory key (eyalroz/libgiddy rebuilt for sm_100a by oracle/build_ref.sh), on the same resident column, rank 0."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libgiddy_ref.so")
+    if not os.path.exists(path):
+        return {"unavailable": "oracle/_ref/libgiddy_ref.so has not been built"}
+    try:
+        kernel = g.Library(path).produce_subclass(KEY)
+        steps = max(3, min(args.steps, 20))
+        config = None
+        for _ in range(3):
+            config = kernel.resolve_launch_configuration(resolve_arguments)
+            kernel.enqueue_launch(None, config, launch_arguments)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        start.record()
+        for _ in range(steps):
+            config = kernel.resolve_launch_configuration(resolve_arguments)
+            kernel.enqueue_launch(None, config, launch_arguments)
+        end.record()
+        torch.cuda.synchronize()
+        seconds = start.elapsed_time(end) / 1e3 / steps
+        return {"value": column["n"] * 4 / seconds / 1e9, "unit": "GB/s", "ms_per_step": seconds * 1e3, "steps": steps,
+                "algorithmic_gbs": algorithmic_bytes(column) / seconds / 1e9,
+                "launch": {"grid": config.grid, "block": config.block, "dynamic_shared_memory": config.dynamic_shared_memory_size},
+                "what": "eyalroz/libgiddy's own run_length_encoding::decompress kernel + resolver, rebuilt for sm_100a, same column"}
+    except Exception as error:
+        return {"unavailable": str(error)[:200]}
 
 
 def run_e2e(args, torch, np, g, columns, kernel, column, out, device, distributed, world):

@@ -45,6 +45,7 @@ def workloads(log2_n):
     w.append(("DZB-fixed u32<-u16", lambda: cases.dzbf_case(1, n, 4, 2)))
     w.append(("DZB-fixed u64<-u8", lambda: cases.dzbf_case(1, n // 2, 8, 1)))
     w.append(("cfg4 DZB-variable u32 2-bit sizes L=1024", lambda: cases.dzbv_case(1, n, 1024, 4, 4, 2, 1)))
+    w.append(("cfg4 fused Delta(DZB-variable) u64<-u32 L=1024", lambda: cases.dzbv_delta_case(1, n // 2, 1024, 8, 4, 4, 2, 1)))
     w.append(("cfg5 Incidence bitmaps u32 K=16", lambda: cases.bitmaps_case(1, n, 4, 16)))
     w.append(("cfg3 scatter u64 1% patches", lambda: cases.scatter_case(1, n // 2, n // 200, 8, 4, 4)))
     w.append(("cfg5 ci-scatter u32 1% patches A=1024", lambda: cases.ci_scatter_case(1, n, n // 100, 4, 4, 4, 1024)))

@@ -815,6 +815,104 @@ const device_function_t kernel_t<I, U, CS>::get_device_function() const { return
 } // namespace discard_zero_bytes
 
 // =================================================================================================
+// Extensions: fused composite decoders (keys under decompression::composite::; no reference counterpart)
+// =================================================================================================
+namespace composite {
+
+/// Delta applied to the output of DZB-variable in one pass (BASELINE.json configs[3]).  Argument maps: the union
+/// of the two schemes' (reference delta.cu:55-56,73-77 and discard_zero_bytes_variable.cu:58-61,80-89), with
+/// "position_anchors" the byte-offset anchors of the DZB-variable stage and "anchor_values" those of the Delta stage.
+namespace delta_of_discard_zero_bytes_variable_width {
+
+using element_size_t = unsigned;
+
+template <unsigned IndexSize, unsigned UncompressedSize, unsigned CompressedSize, unsigned ElementSizesContainerSize>
+class launch_config_resolution_params_t final : public kernels::launch_config_resolution_params_t {
+public:
+	using parent = kernels::launch_config_resolution_params_t;
+	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t length_in_elements, ::std::size_t segment_length,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes,
+			giddy_b200_delta_of_discard_zero_bytes_variable_kernel(IndexSize, UncompressedSize, CompressedSize, ElementSizesContainerSize)))
+	{
+		if (segment_length == 0) { throw ::std::invalid_argument("The segment length must be a positive number"); }
+		detail::configure_warp_per_unit(*this, util::div_rounding_up(length_in_elements, segment_length), GIDDY_SEGMENT_WARPS_PER_BLOCK);
+		dynamic_shared_memory_requirement.per_length_unit = GIDDY_DZBV_SHARED_BYTES_PER_WARP(CompressedSize) / warp_size;
+	}
+};
+
+template <unsigned IndexSize, unsigned UncompressedSize, unsigned CompressedSize, unsigned ElementSizesContainerSize>
+class kernel_t : public cuda::registered::kernel_t {
+public:
+	GIDDY_WRAPPER_BOILERPLATE;
+	using uncompressed_type                  = uint_t<UncompressedSize>;
+	using element_sizes_container_size_type  = uint_t<ElementSizesContainerSize>;
+	using index_type                         = uint_t<IndexSize>;
+
+	static ::std::string key()
+	{
+		return "decompression::composite::delta_of_discard_zero_bytes_variable_width::kernel_t<" + detail::u(IndexSize) + ", " +
+			detail::u(UncompressedSize) + ", " + detail::u(CompressedSize) + ", " + detail::u(ElementSizesContainerSize) + ">";
+	}
+
+	launch_configuration_t resolve_launch_configuration(
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
+		::std::size_t length, ::std::size_t segment_length,
+		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
+	{
+		launch_config_resolution_params_t<IndexSize, UncompressedSize, CompressedSize, ElementSizesContainerSize> params(
+			device_properties, length, segment_length, optional<device_function::attributes_t>(kernel_function_attributes));
+		return kernels::resolve_launch_configuration(params, limits);
+	}
+
+	void enqueue_launch(stream::id_t stream, const launch_configuration_t& launch_config,
+		uncompressed_type* decompressed, const unsigned char* compressed_data, const element_sizes_container_size_type* packed_element_sizes,
+		const index_type* position_anchors, const uncompressed_type* anchor_values, index_type segment_length, index_type length,
+		element_size_t min_represented_element_size, unsigned bits_per_element_size) const
+	{
+		auto config = to_c(launch_config);
+		cuda::detail::throw_if_error(giddy_b200_delta_of_discard_zero_bytes_variable_launch(stream, &config,
+			IndexSize, UncompressedSize, CompressedSize, ElementSizesContainerSize, decompressed, compressed_data, packed_element_sizes,
+			position_anchors, anchor_values, segment_length, length, min_represented_element_size, bits_per_element_size));
+	}
+};
+
+template <unsigned I, unsigned U, unsigned C, unsigned CS>
+launch_configuration_t kernel_t<I, U, C, CS>::resolve_launch_configuration(
+	device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
+	arguments_type extra_arguments, launch_configuration_limits_t limits) const
+{
+	auto length         = detail::required<::std::size_t>(extra_arguments, "length");
+	auto segment_length = detail::required<::std::size_t>(extra_arguments, "segment_length");
+	return resolve_launch_configuration(device_properties, kernel_function_attributes, length, segment_length, limits);
+}
+
+template <unsigned I, unsigned U, unsigned C, unsigned CS>
+void kernel_t<I, U, C, CS>::enqueue_launch(stream::id_t stream, const launch_configuration_t& launch_config, arguments_type arguments) const
+{
+	auto decompressed                 = detail::required<uncompressed_type*>(arguments, "decompressed");
+	auto compressed_data              = detail::required<const unsigned char*>(arguments, "compressed_data");
+	auto packed_element_sizes         = detail::required<const element_sizes_container_size_type*>(arguments, "packed_element_sizes");
+	auto position_anchors             = detail::required<const index_type*>(arguments, "position_anchors");
+	auto anchor_values                = detail::required<const uncompressed_type*>(arguments, "anchor_values");
+	auto segment_length               = detail::required<index_type>(arguments, "segment_length");
+	auto length                       = detail::required<index_type>(arguments, "length");
+	auto min_represented_element_size = detail::required<element_size_t>(arguments, "min_represented_element_size");
+	auto bits_per_element_size        = detail::required<unsigned>(arguments, "bits_per_element_size");
+	enqueue_launch(stream, launch_config, decompressed, compressed_data, packed_element_sizes, position_anchors, anchor_values,
+		segment_length, length, min_represented_element_size, bits_per_element_size);
+}
+
+template <unsigned I, unsigned U, unsigned C, unsigned CS>
+const device_function_t kernel_t<I, U, C, CS>::get_device_function() const
+{
+	return giddy_b200_delta_of_discard_zero_bytes_variable_kernel(I, U, C, CS);
+}
+
+} // namespace delta_of_discard_zero_bytes_variable_width
+} // namespace composite
+
+// =================================================================================================
 // Incidence bitmaps -- reference src/kernel_wrappers/decompression/incidence_bitmaps.cu:13-102
 // =================================================================================================
 namespace incidence_bitmaps {

@@ -329,6 +329,26 @@ GIDDY_API giddy_status_t giddy_b200_compressed_indices_scatter_launch(
 	const void* scatter_position_anchors,
 	uint64_t anchoring_period, uint64_t num_scatter_position_runs, uint64_t data_length);
 
+/* ------------------------------------------------------------------------- */
+/* Extensions: fused composite decoders (no counterpart kernel in the          */
+/* reference, which composes schemes by running one kernel after another,      */
+/* README.md:55-60).                                                           */
+/* ------------------------------------------------------------------------- */
+
+/* delta::decompress<IndexSize, UncompressedSize, CompressedSize> (src/kernels/decompression/delta.cuh:66-108) applied to
+ * the output of discard_zero_bytes::variable_width::decompress<IndexSize, CompressedSize, ElementSizesContainerSize>
+ * (src/kernels/decompression/discard_zero_bytes_variable.cuh:381-439), same segment length for both, in one pass:
+ *   decompressed[i] = anchor_values[s] + sum_{j = s*L .. i} dzbv_element[j]
+ * Needs 1-, 2- or 4-bit size fields and segment_length * bits_per_element_size % 32 == 0. */
+GIDDY_API const void* giddy_b200_delta_of_discard_zero_bytes_variable_kernel(
+	unsigned index_size, unsigned uncompressed_size, unsigned compressed_size, unsigned element_sizes_container_size);
+GIDDY_API giddy_status_t giddy_b200_delta_of_discard_zero_bytes_variable_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned index_size, unsigned uncompressed_size, unsigned compressed_size, unsigned element_sizes_container_size,
+	void* decompressed, const void* compressed_data, const void* packed_element_sizes, const void* position_anchors,
+	const void* anchor_values, uint64_t segment_length, uint64_t length,
+	unsigned min_represented_element_size, unsigned bits_per_element_size);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

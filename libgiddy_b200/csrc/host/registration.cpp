@@ -117,6 +117,13 @@ void register_all_wrappers()
 	}
 #undef GIDDY_REGISTER_SCATTER
 #undef GIDDY_REGISTER_SCATTER_E
+	// Extensions (no reference counterpart): fused composite decoders
+	{
+		using namespace decompression::composite::delta_of_discard_zero_bytes_variable_width;
+		kernel_t<4, 8, 4, 4>::registerInSubclassFactory(); kernel_t<4, 8, 4, 8>::registerInSubclassFactory();
+		kernel_t<4, 8, 2, 4>::registerInSubclassFactory(); kernel_t<4, 4, 2, 4>::registerInSubclassFactory();
+		kernel_t<8, 8, 4, 4>::registerInSubclassFactory();
+	}
 }
 
 } // namespace host

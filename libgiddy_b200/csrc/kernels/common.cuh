@@ -107,6 +107,13 @@ __device__ __forceinline__ void store_streaming_16(void* p, const uint4& v)
 	asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// 256-bit streaming store (sm_100: STG.E.EF.ENL2.256); p must be 32-byte aligned
+__device__ __forceinline__ void store_streaming_32(void* p, const uint32_t (&w)[8])
+{
+	asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+		:: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
 // A register-resident group of Bytes bytes, loadable in one (or a few) maximal-width
 // streaming accesses and addressable as elements of any power-of-2 size.
 template <unsigned Bytes>

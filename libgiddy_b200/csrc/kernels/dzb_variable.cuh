@@ -276,11 +276,29 @@ __device__ __forceinline__ byte_pack<16> assemble_vector(const uint8_t* data, un
 	return vec;
 }
 
+// What becomes of the decoded vectors.  emit() is called by all lanes of the warp together, once per row of 32 x E
+// elements, with `position` the index within the segment of this lane's first element, `vec` its E elements (zeros
+// from index `valid` on) and `valid` in [0, E] the number of them which lie inside the segment.
+template <unsigned U>
+struct store_sink {
+	static constexpr unsigned E = 16 / U;
+	uint_t<U>* out; // the segment's first output element; 16-byte aligned
+
+	__device__ __forceinline__ void emit(uint64_t position, const byte_pack<16>& vec, unsigned valid) const
+	{
+		if (valid == E) { store_pack_16(out + position, vec); }
+		else {
+			#pragma unroll
+			for (unsigned j = 0; j < E; j++) { if (j < valid) { out[position + j] = vec.template get<U>(j); } }
+		}
+	}
+};
+
 // Decode one segment, tile by tile.  Requires: bits in {1, 2, 4}; (first_element * bits) % 32 == 0;
-// `out` 16-byte aligned; packed sizes readable as 32-bit words up to num_field_words.
-template <unsigned U, unsigned bits, typename Offset>
+// packed sizes readable as 32-bit words up to num_field_words.
+template <unsigned U, unsigned bits, typename Sink>
 __device__ __forceinline__ void decode_segment_staged(
-	uint_t<U>*        __restrict__  out,              // the segment's first output element
+	Sink&                           sink,
 	const uint8_t*    __restrict__  compressed_data,
 	uint64_t                        segment_first_byte,
 	bool                            next_anchor_known,
@@ -398,35 +416,33 @@ __device__ __forceinline__ void decode_segment_staged(
 		// 3. expand
 		const unsigned head = (unsigned)((reinterpret_cast<uintptr_t>(compressed_data) + tile_first_byte) & 15u);
 		const uint8_t* const bytes = tile.data; // 16-byte aligned; the tile's first byte is bytes[head]
-		uint_t<U>* const tile_out = out + tile_start;
 		if (tile_length == tile_elements) { // a full tile: every offset below is an immediate
 			constexpr unsigned words_per_row = warp_size * E * bits / 32;
 			const uint16_t* lane_offsets = tile.offsets + lane;
 			const uint32_t* lane_fields = tile.fields + (lane * E * bits) / 32;
 			const unsigned field_shift = (lane * E * bits) % 32;
-			uint_t<U>* lane_out = tile_out + lane * E;
 			#pragma unroll
 			for (unsigned row = 0; row < tile_elements / (warp_size * E); row++) {
 				const unsigned at = head + lane_offsets[row * warp_size];
 				const uint32_t chunk = lane_fields[row * words_per_row] >> field_shift;
-				store_pack_16(lane_out + row * warp_size * E, assemble_vector<U, bits>(bytes, at, chunk, min_size));
+				sink.emit(tile_start + (row * warp_size + lane) * E, assemble_vector<U, bits>(bytes, at, chunk, min_size), E);
 			}
 		}
 		else {
 			const unsigned num_rows = (tile_length + warp_size * E - 1) / (warp_size * E);
-			for (unsigned row = 0; row < num_rows; row++) {
+			for (unsigned row = 0; row < num_rows; row++) { // (warp-uniform trip count: sinks may use warp collectives)
 				const unsigned vector = row * warp_size + lane;
 				const unsigned p = vector * E;
-				if (p >= tile_length) { break; }
+				const unsigned valid = (p < tile_length) ? minimum<unsigned>(E, tile_length - p) : 0u;
 				const unsigned at = head + tile.offsets[vector];
 				const unsigned first_bit = p * bits;
 				const uint32_t chunk = tile.fields[first_bit / 32] >> (first_bit % 32);
-				const byte_pack<16> vec = assemble_vector<U, bits>(bytes, at, chunk, min_size);
-				if (p + E <= tile_length) { store_pack_16(tile_out + p, vec); }
-				else {
+				byte_pack<16> vec = assemble_vector<U, bits>(bytes, at, chunk, min_size);
+				if (valid < E) {
 					#pragma unroll
-					for (unsigned j = 0; j < E; j++) { if (p + j < tile_length) { tile_out[p + j] = vec.template get<U>(j); } }
+					for (unsigned j = 0; j < E; j++) { if (j >= valid) { vec.template set<U>(j, 0); } }
 				}
+				sink.emit(tile_start + p, vec, valid);
 			}
 		}
 		__syncwarp(); // the tile's shared memory is free again
@@ -482,17 +498,18 @@ __global__ void __launch_bounds__(GIDDY_SEGMENT_WARPS_PER_BLOCK * 32, GIDDY_DZBV
 			const uint64_t first_byte = __ldg(position_anchors + segment);
 			const bool next_anchor_known = segment + 1 < num_segments;
 			const uint64_t next_anchor = next_anchor_known ? (uint64_t) __ldg(position_anchors + segment + 1) : 0;
+			store_sink<U> sink { decompressed + start };
 			switch (bits) {
 			case 1:
-				decode_segment_staged<U, 1, offset_t>(decompressed + start, compressed_data, first_byte, next_anchor_known, next_anchor,
+				decode_segment_staged<U, 1>(sink, compressed_data, first_byte, next_anchor_known, next_anchor,
 					field_words, num_field_words, start, this_length, min_represented_element_size, tile, barrier_phase);
 				break;
 			case 2:
-				decode_segment_staged<U, 2, offset_t>(decompressed + start, compressed_data, first_byte, next_anchor_known, next_anchor,
+				decode_segment_staged<U, 2>(sink, compressed_data, first_byte, next_anchor_known, next_anchor,
 					field_words, num_field_words, start, this_length, min_represented_element_size, tile, barrier_phase);
 				break;
 			default:
-				decode_segment_staged<U, (E * 4 <= 32 ? 4 : 2), offset_t>(decompressed + start, compressed_data, first_byte, next_anchor_known, next_anchor,
+				decode_segment_staged<U, (E * 4 <= 32 ? 4 : 2)>(sink, compressed_data, first_byte, next_anchor_known, next_anchor,
 					field_words, num_field_words, start, this_length, min_represented_element_size, tile, barrier_phase);
 				break;
 			}

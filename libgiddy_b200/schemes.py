@@ -248,6 +248,34 @@ def discard_zero_bytes_variable(decompressed, compressed_data, packed_element_si
                 stream, limits)
 
 
+def delta_of_discard_zero_bytes_variable_key(index_size, uncompressed_size, compressed_size, container_size=4):
+    return "decompression::composite::delta_of_discard_zero_bytes_variable_width::kernel_t<%du, %du, %du, %du>" % (
+        index_size, uncompressed_size, compressed_size, container_size)
+
+
+def delta_of_discard_zero_bytes_variable(decompressed, compressed_data, packed_element_sizes, position_anchors, anchor_values,
+                                         segment_length, length, min_represented_element_size, bits_per_element_size, *,
+                                         uncompressed_size, compressed_size, container_size=4, index_size=4,
+                                         stream=None, limits=None, library=None):
+    """Extension: Delta applied to the output of DZB-variable in one pass (no reference counterpart)."""
+    _check_size(decompressed, uncompressed_size, "decompressed")
+    _check_size(anchor_values, uncompressed_size, "anchor_values")
+    _check_size(packed_element_sizes, container_size, "packed_element_sizes")
+    _check_size(position_anchors, index_size, "position_anchors")
+    index = N.uint_of_size(index_size)
+    return _run(library, delta_of_discard_zero_bytes_variable_key(index_size, uncompressed_size, compressed_size, container_size),
+                {"length": N.size_t(length), "segment_length": N.size_t(segment_length)},
+                {"decompressed": N.ptr(decompressed, _UTAG[uncompressed_size]),
+                 "compressed_data": N.cptr(compressed_data, "u8"),
+                 "packed_element_sizes": N.cptr(packed_element_sizes, _UTAG[container_size]),
+                 "position_anchors": N.cptr(position_anchors, _UTAG[index_size]),
+                 "anchor_values": N.cptr(anchor_values, _UTAG[uncompressed_size]),
+                 "segment_length": index(segment_length), "length": index(length),
+                 "min_represented_element_size": N.unsigned(min_represented_element_size),
+                 "bits_per_element_size": N.unsigned(bits_per_element_size)},
+                stream, limits)
+
+
 def incidence_bitmaps(decompressed, bitmaps, dictionary_entries, length, bitmap_length, num_bitmaps, *,
                       uncompressed_size, alignment_in_ints=2, use_dictionary=True, index_size=4,
                       stream=None, limits=None, library=None):

@@ -227,6 +227,36 @@ def dzbv_case(seed, n, L, U, CS, bits, min_size, I=4, ref_ok=None):
                 expected, launch, ref_ok=(n % L == 0) if ref_ok is None else ref_ok)
 
 
+def dzbv_delta_case(seed, n, L, U, C, CS, bits, min_size, I=4):
+    """The fused extension: Delta applied to DZB-variable-compressed deltas.  Expected output: the oracle's two decoders chained."""
+    r = rng(12, seed, n, L, U, C, CS, bits)
+    max_size = min(C, min_size + (1 << bits) - 1)
+    widths = r.integers(min_size, max_size + 1, n)
+    deltas = np.zeros(n, dtype=UINT[C])
+    raw = random_uint(r, C, n)
+    for w in range(1, C + 1):
+        mask = widths == w
+        deltas[mask] = raw[mask] >> UINT[C](8 * (C - w)) if w < C else raw[mask]
+    base = int(random_uint(r, U, 1)[0])
+    column = (np.cumsum(deltas.astype(np.uint64), dtype=np.uint64) + np.uint64(base)).astype(UINT[U])
+    delta_encoded = E.delta_encode(column, L, C, base)
+    assert (delta_encoded["compressed_input"] == deltas).all()
+    enc = E.discard_zero_bytes_variable_encode(deltas, L, CS, bits, min_size, I)
+    enc.pop("element_sizes")
+    enc["compressed_data"] = np.concatenate((enc["compressed_data"], np.zeros(8, np.uint8)))
+    widened = O.discard_zero_bytes_variable(enc["compressed_data"], enc["packed_element_sizes"], enc["position_anchors"], L, n, min_size, bits, C)
+    expected = O.delta(widened, delta_encoded["anchor_values"], n, L)
+    assert (expected == column).all()
+    inputs = dict(enc, anchor_values=delta_encoded["anchor_values"])
+
+    def launch(out, t, library, limits):
+        S.delta_of_discard_zero_bytes_variable(out, t["compressed_data"], t["packed_element_sizes"], t["position_anchors"], t["anchor_values"],
+                                               L, n, min_size, bits, uncompressed_size=U, compressed_size=C, container_size=CS, index_size=I,
+                                               library=library, limits=limits)
+    return Case("dzbv+delta-I%d-U%d-C%d-CS%d-b%d-m%d-n%d-L%d" % (I, U, C, CS, bits, min_size, n, L), "delta_of_discard_zero_bytes_variable",
+                inputs, dict(n=n, L=L), expected, launch, ref_ok=False)
+
+
 def bitmaps_case(seed, n, U, K, use_dictionary=True, I=4, alignment=2):
     r = rng(9, seed, n, U, K)
     indices = r.integers(0, K, n)
@@ -364,6 +394,15 @@ def all_cases():
     cases.append(dzbv_case(12, 33000, 1024, 4, 4, 4, 0, ref_ok=False))
     cases.append(dzbv_case(13, 64 * 1024, 1024, 8, 4, 2, 5, ref_ok=False))
     cases.append(dzbv_case(14, 20, 1024, 4, 4, 2, 1, ref_ok=False))
+    # Extension: Delta of DZB-variable, fused (5 keys)
+    for (I, U, C, CS) in [(4, 8, 4, 4), (4, 8, 4, 8), (4, 8, 2, 4), (4, 4, 2, 4), (8, 8, 4, 4)]:
+        bits = 2 if C == 4 else 1
+        cases.append(dzbv_delta_case(0, 32 * 1024, 1024, U, C, CS, bits, 1, I))
+    cases.append(dzbv_delta_case(1, 50000 + 3, 1008, 8, 4, 4, 2, 1))      # partial tiles, ragged tail
+    cases.append(dzbv_delta_case(2, 5 * 4096, 4096, 8, 4, 4, 2, 0))       # several tiles per segment, zero-size deltas
+    cases.append(dzbv_delta_case(3, 4000 + 5, 16, 8, 4, 4, 2, 1))         # tiny segments
+    cases.append(dzbv_delta_case(4, 33000, 1024, 8, 4, 4, 4, 0))          # 4-bit fields
+    cases.append(dzbv_delta_case(5, 1 << 20, 1024, 8, 4, 4, 2, 1))
     # Incidence bitmaps (5 keys)
     for (U, use_dictionary) in [(1, True), (2, True), (4, True), (8, True), (1, False)]:
         cases.append(bitmaps_case(0, 64 * 1024, U, 16, use_dictionary))
