@@ -278,6 +278,10 @@ def run_product_arm(args):
         raise SystemExit("bench.py needs a CUDA device: libgiddy_b200 has no CPU path (use --impl reference for the host decoder)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_node = None
+    if distributed:  # pinned buffers of the host-resident leg should live on the socket this rank's GPU hangs off
+        from libgiddy_b200 import hostmem
+        numa_node = hostmem.bind_to_numa_node_of_gpu(local_rank)
     if distributed:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -391,7 +395,7 @@ def run_product_arm(args):
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "verified_bit_exact": verified,
-            "reference_kernels": reference_kernels,
+            "reference_kernels": reference_kernels, "numa_node_rank0": numa_node,
             "algorithmic_gbs_all_gpus": algorithmic_total * args.steps / seconds / 1e9,
             "library": library.version(),
         }))

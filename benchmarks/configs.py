@@ -549,6 +549,8 @@ def main():
     torch.cuda.set_device(LOCAL_RANK)
     device = torch.device("cuda", LOCAL_RANK)
     if WORLD > 1:
+        from libgiddy_b200 import hostmem
+        hostmem.bind_to_numa_node_of_gpu(LOCAL_RANK)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=device)
     product = g.default_library()
