@@ -202,6 +202,24 @@ def cfg3(args, device, product, reference, rows, peak):
     report(rows, peak, "cfg3", "Dictionary + scatter, two kernels " + name, n * 8, decode_bytes + patch_bytes, seconds, verified,
            with_reference(reference, both, args.repeats))
 
+    # extension: the same column decoded and patched in one pass
+    def fused(limits=None):
+        S.patched_dictionary(out, indices, dictionary, n, 256, patches, positions32, p, uncompressed_size=8, dictionary_index_size=1, limits=limits)
+    out.zero_()
+    fused()
+    expected = dictionary[indices.to(torch.int64)]
+    expected[positions] = patches
+    verified_fused = bool(torch.equal(out, expected))
+    del expected
+    fused_bytes = decode_bytes + nbytes(patches, positions32)
+    seconds = time_passes(fused, args.repeats)
+    report(rows, peak, "cfg3", "fused patched Dictionary, one kernel " + name, n * 8, fused_bytes, seconds, verified_fused, extra={"extension": True})
+    if args.sweep_grids:
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        for per_sm in (4, 8, 16, 64, 128):
+            seconds = time_passes(lambda: fused({"grid_size": sms * per_sm}), args.repeats)
+            report(rows, peak, "cfg3", "fused patched Dictionary, %d CTAs/SM" % per_sm, n * 8, fused_bytes, seconds, verified_fused, extra={"extension": True})
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # cfg4: Delta int64 (anchored) over DZB-variable deltas (1-4 bytes, 2-bit size fields), L = 1024
@@ -353,6 +371,27 @@ def cfg5(args, device, product, reference, rows, peak):
     seconds = time_passes(ci_patch, args.repeats)
     report(rows, peak, "cfg5", "A: ci-scatter alone (p=%d)" % p, p * 4, nbytes(patch_values, *ci.values()) - 16 + p * 4, seconds, verified_a,
            with_reference(reference, ci_patch, args.repeats))
+
+    # extension: column A decoded and patched in one pass
+    def fused_a(limits=None):
+        S.patched_frame_of_reference(out_a, offsets, coefficients, n, L, patch_values, ci["run_lengths"], ci["offset_sizes"], ci["baselines"],
+                                     ci["offsets_start"], ci["offset_bytes"], ci["anchors"], A, num_runs, p,
+                                     uncompressed_size=4, compressed_size=2, model="linear", limits=limits)
+    out_a.zero_()
+    fused_a()
+    x = torch.arange(L, device=device, dtype=torch.int32).repeat(S_)
+    expected = coefficients[:, 0].repeat_interleave(L) + coefficients[:, 1].repeat_interleave(L) * x + offsets.to(torch.int32)
+    del x
+    expected[positions] = patch_values
+    verified_fused = bool(torch.equal(out_a, expected))
+    del expected
+    seconds = time_passes(fused_a, args.repeats)
+    report(rows, peak, "cfg5", "A: fused patched FOR (ci patches), one kernel", n * 4, bytes_a + n * 4, seconds, verified_fused, extra={"extension": True})
+    if args.sweep_grids:
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        for per_sm in (4, 8, 16, 64, 128):
+            seconds = time_passes(lambda: fused_a({"grid_size": sms * per_sm}), args.repeats)
+            report(rows, peak, "cfg5", "A: fused patched FOR, %d CTAs/SM" % per_sm, n * 4, bytes_a + n * 4, seconds, verified_fused, extra={"extension": True})
 
     # (B) RPE, absolute positions, mean run 64
     gen = generator(device, 23)
@@ -543,6 +582,7 @@ def main():
     parser.add_argument("--streams", type=int, default=4)
     parser.add_argument("--cfg4-columns", type=int, default=8, help="columns of cfg4 spread over the ranks (1 per GPU at 8 GPUs)")
     parser.add_argument("--no-reference", action="store_true")
+    parser.add_argument("--sweep-grids", action="store_true", help="also time the fused patched decoders under several grid sizes")
     parser.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.json"))
     args = parser.parse_args()
 

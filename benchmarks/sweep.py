@@ -40,6 +40,9 @@ def workloads(log2_n):
     w.append(("RPE u32 rel run16 L=1024", lambda: cases.rpe_case(1, n, 1024, 4, 2, True, avoid_boundary_runs=True)))
     w.append(("cfg4 Delta u64<-u32 L=1024", lambda: cases.delta_case(1, n // 2, 1024, 8, 4)))
     w.append(("Delta u32<-u8 L=1024", lambda: cases.delta_case(1, n, 1024, 4, 1)))
+    w.append(("Delta u64<-u32 long segments L=2^20 (look-back)", lambda: cases.delta_case(1, n // 2, 1 << 20, 8, 4)))
+    w.append(("Delta u64<-u32 one segment (look-back)", lambda: cases.delta_case(1, n // 2, n // 2, 8, 4)))
+    w.append(("Delta u32<-u8 one segment (look-back)", lambda: cases.delta_case(1, n, n, 4, 1)))
     w.append(("cfg3 Dictionary u64<-u8 D=256", lambda: cases.dictionary_case(1, n // 2, 8, 1, 256)))
     w.append(("Dictionary u32<-u16 D=60000 (L2 gather)", lambda: cases.dictionary_case(1, n, 4, 2, 60000, cache=False)))
     w.append(("DZB-fixed u32<-u16", lambda: cases.dzbf_case(1, n, 4, 2)))
@@ -48,6 +51,9 @@ def workloads(log2_n):
     w.append(("cfg4 fused Delta(DZB-variable) u64<-u32 L=1024", lambda: cases.dzbv_delta_case(1, n // 2, 1024, 8, 4, 4, 2, 1)))
     w.append(("cfg5 Incidence bitmaps u32 K=16", lambda: cases.bitmaps_case(1, n, 4, 16)))
     w.append(("cfg3 scatter u64 1% patches", lambda: cases.scatter_case(1, n // 2, n // 200, 8, 4, 4)))
+    w.append(("cfg3 fused patched Dictionary u64<-u8 1%", lambda: cases.patched_dictionary_case(1, n // 2, 8, 1, 256, n // 200)))
+    w.append(("fused patched Dictionary u32<-u8 5%", lambda: cases.patched_dictionary_case(1, n, 4, 1, 256, n // 20)))
+    w.append(("cfg5 fused patched FOR i32<-i16 linear ci 1%", lambda: cases.patched_for_case(1, n, 1024, 4, 2, "linear", n // 100, 1024)))
     w.append(("cfg5 ci-scatter u32 1% patches A=1024", lambda: cases.ci_scatter_case(1, n, n // 100, 4, 4, 4, 1024)))
     return w
 

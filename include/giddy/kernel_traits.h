@@ -35,4 +35,24 @@
 #define GIDDY_SCATTER_BLOCK_THREADS 256
 #define GIDDY_CI_SCATTER_WARPS_PER_BLOCK 4
 
+/* Delta: a lane scans this many rows of 16-byte vectors per step.  Columns with few, long segments (so that a warp per
+ * segment could not fill the GPU) are decoded tile by tile with decoupled look-back instead: CTAs of this many threads,
+ * tiles of threads * rows * (16 / U) elements, persistent CTAs fed by a ticket counter. */
+#define GIDDY_DELTA_ROWS_PER_STEP 4
+#define GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS 256
+#define GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR 8
+#define GIDDY_DELTA_TILE_ELEMENTS(U, threads) ((threads) * GIDDY_DELTA_ROWS_PER_STEP * (16 / (U)))
+#define GIDDY_DELTA_USES_LOOK_BACK(length, segment_length, U) \
+	((segment_length) >= 4 * GIDDY_DELTA_TILE_ELEMENTS(U, GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS) && \
+	 ((length) + (segment_length) - 1) / (segment_length) < 8192)
+
+/* Patched decoders (decode + patches in one pass): every warp owns a contiguous range of warp tiles (32 x
+ * GIDDY_ELEMENTWISE_UNROLL vectors each); CTAs of at most this many threads; this many CTAs per multiprocessor are
+ * asked for (several waves, so that each warp's one-off patch seek and the last wave's imbalance stay small against
+ * its streaming work); compressed patch positions are decoded this many at a time into each warp's slice of (static)
+ * shared memory. */
+#define GIDDY_PATCHED_BLOCK_THREADS 256
+#define GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR 32
+#define GIDDY_PATCHED_WINDOW 128
+
 #endif /* GIDDY_KERNEL_TRAITS_H_ */

@@ -477,6 +477,19 @@ public:
 		parent(device_properties_, detail::attributes_or_query(known_attributes, giddy_b200_delta_kernel(IndexSize, UncompressedSize, CompressedSize)))
 	{
 		if (segment_length == 0) { throw ::std::invalid_argument("The segment length must be a positive number"); }
+		if (GIDDY_DELTA_USES_LOOK_BACK(data_length, segment_length, UncompressedSize)) {
+			// few, long segments: tiles scanned with decoupled look-back by persistent CTAs fed from a ticket counter;
+			// any grid is correct, one resident wave is what is wanted
+			const ::std::size_t tile = GIDDY_DELTA_TILE_ELEMENTS(UncompressedSize, GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS);
+			grid_construction_resolution  = block;
+			serialization_option          = auto_maximized;
+			length                        = util::div_rounding_up(data_length, tile);
+			quanta.threads_in_block       = warp_size;
+			upper_limits.threads_in_block = GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS;
+			block_resolution_constraints.max_threads_per_block = GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS;
+			keep_gpu_busy_factor          = GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR * (GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS / warp_size) / 4;
+			return;
+		}
 		detail::configure_warp_per_unit(*this, util::div_rounding_up(data_length, segment_length), GIDDY_SEGMENT_WARPS_PER_BLOCK);
 	}
 };
@@ -910,6 +923,238 @@ const device_function_t kernel_t<I, U, C, CS>::get_device_function() const
 }
 
 } // namespace delta_of_discard_zero_bytes_variable_width
+
+namespace detail_patched {
+
+/// The launch-configuration policy shared by the patched decoders: block resolution, CTAs of GIDDY_PATCHED_BLOCK_THREADS
+/// threads each owning a contiguous range of tiles, GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR of them per multiprocessor
+/// (fewer when the column has fewer tiles).  The kernels are correct under any grid and any whole-warp block.
+inline void configure(launch_config_resolution_params_t& p, ::std::size_t length_in_elements, unsigned uncompressed_size)
+{
+	const ::std::size_t elements_per_tile = (::std::size_t) GIDDY_PATCHED_BLOCK_THREADS * GIDDY_ELEMENTWISE_UNROLL * (16 / uncompressed_size);
+	p.grid_construction_resolution  = launch_config_resolution_params_t::block;
+	p.serialization_option          = launch_config_resolution_params_t::auto_maximized;
+	p.length                        = util::div_rounding_up(length_in_elements, elements_per_tile);
+	p.quanta.threads_in_block       = warp_size;
+	p.upper_limits.threads_in_block = GIDDY_PATCHED_BLOCK_THREADS;
+	p.block_resolution_constraints.max_threads_per_block = GIDDY_PATCHED_BLOCK_THREADS;
+	// blocks = multiprocessors x warp schedulers (4) x factor / warps per block
+	p.keep_gpu_busy_factor          = GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR * (GIDDY_PATCHED_BLOCK_THREADS / warp_size) / 4;
+}
+
+} // namespace detail_patched
+
+/// Dictionary decode and naive patching in one pass (BASELINE.json configs[2]): the argument maps of
+/// decompression::dictionary (reference dictionary.cu:57-60,77-90) plus the patches of scatter (scatter.cu:55,70-73)
+/// under the names "patch_data", "patch_indices" (ascending positions of type uint_t<IndexSize>) and "num_patches".
+namespace patched_dictionary {
+
+template <unsigned IndexSize, unsigned UncompressedSize, unsigned DictionaryIndexSize>
+class launch_config_resolution_params_t final : public kernels::launch_config_resolution_params_t {
+public:
+	using parent = kernels::launch_config_resolution_params_t;
+	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t num_dictionary_entries,
+		::std::size_t data_length, optional<bool> cache_dictionary_in_shared_memory_override = nullopt,
+		optional<shared_memory_size_t> dynamic_shared_mem_limit = nullopt,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes,
+			giddy_b200_patched_dictionary_kernel(IndexSize, UncompressedSize, DictionaryIndexSize)), dynamic_shared_mem_limit)
+	{
+		const ::std::size_t dictionary_bytes = num_dictionary_entries * UncompressedSize;
+		const bool worthwhile = dictionary_bytes <= dictionary::max_default_cached_dictionary_bytes &&
+			dictionary_bytes <= available_dynamic_shared_memory_per_block && data_length * UncompressedSize >= 64 * dictionary_bytes;
+		detail_patched::configure(*this, data_length, UncompressedSize);
+		if (cache_dictionary_in_shared_memory_override.value_or(worthwhile)) {
+			dynamic_shared_memory_requirement.per_block = (shared_memory_size_t) dictionary_bytes;
+		}
+	}
+};
+
+template <unsigned IndexSize, unsigned UncompressedSize, unsigned DictionaryIndexSize>
+class kernel_t : public cuda::registered::kernel_t {
+public:
+	GIDDY_WRAPPER_BOILERPLATE;
+	using dictionary_index_type = uint_t<DictionaryIndexSize>;
+	using dictionary_size_type  = size_type_by_index_size<DictionaryIndexSize>;
+	using uncompressed_type     = uint_t<UncompressedSize>;
+	using index_type            = uint_t<IndexSize>;
+	using size_type             = size_type_by_index_size<IndexSize>;
+
+	static ::std::string key()
+	{
+		return "decompression::composite::patched_dictionary::kernel_t<" + detail::u(IndexSize) + ", " + detail::u(UncompressedSize) + ", " +
+			detail::u(DictionaryIndexSize) + ">";
+	}
+
+	launch_configuration_t resolve_launch_configuration(
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
+		::std::size_t num_dictionary_entries, ::std::size_t data_length, optional<bool> cache_input_data_in_shared_mem = nullopt,
+		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
+	{
+		launch_config_resolution_params_t<IndexSize, UncompressedSize, DictionaryIndexSize> params(device_properties, num_dictionary_entries,
+			data_length, cache_input_data_in_shared_mem, limits.dynamic_shared_memory, optional<device_function::attributes_t>(kernel_function_attributes));
+		return kernels::resolve_launch_configuration(params, limits);
+	}
+
+	void enqueue_launch(stream::id_t stream, const launch_configuration_t& launch_config,
+		uncompressed_type* decompressed, const dictionary_index_type* compressed_input, const uncompressed_type* dictionary_entries,
+		size_type length, dictionary_size_type num_dictionary_entries, bool cache_dictionary_in_shared_mem,
+		const uncompressed_type* patch_data, const index_type* patch_indices, size_type num_patches) const
+	{
+		auto config = to_c(launch_config);
+		cuda::detail::throw_if_error(giddy_b200_patched_dictionary_launch(stream, &config, IndexSize, UncompressedSize, DictionaryIndexSize,
+			decompressed, compressed_input, dictionary_entries, length, num_dictionary_entries, cache_dictionary_in_shared_mem,
+			patch_data, patch_indices, num_patches));
+	}
+};
+
+template <unsigned I, unsigned U, unsigned DI>
+launch_configuration_t kernel_t<I, U, DI>::resolve_launch_configuration(
+	device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
+	arguments_type extra_arguments, launch_configuration_limits_t limits) const
+{
+	auto num_dictionary_entries         = detail::required<::std::size_t>(extra_arguments, "num_dictionary_entries");
+	auto data_length                    = detail::required<::std::size_t>(extra_arguments, "data_length");
+	auto cache_input_data_in_shared_mem = detail::optional_argument<bool>(extra_arguments, "cache_input_data_in_shared_mem");
+	return resolve_launch_configuration(device_properties, kernel_function_attributes, num_dictionary_entries, data_length,
+		cache_input_data_in_shared_mem, limits);
+}
+
+template <unsigned I, unsigned U, unsigned DI>
+void kernel_t<I, U, DI>::enqueue_launch(stream::id_t stream, const launch_configuration_t& launch_config, arguments_type arguments) const
+{
+	auto caching = detail::optional_argument<bool>(arguments, "cache_dictionary_in_shared_mem").value_or(launch_config.dynamic_shared_memory_size > 0);
+	auto decompressed           = detail::required<uncompressed_type*>(arguments, "decompressed");
+	auto compressed_input       = detail::required<const dictionary_index_type*>(arguments, "compressed_input");
+	auto dictionary_entries     = detail::required<const uncompressed_type*>(arguments, "dictionary_entries");
+	auto length                 = detail::required<size_type>(arguments, "length");
+	auto num_dictionary_entries = detail::required<dictionary_size_type>(arguments, "num_dictionary_entries");
+	auto patch_data             = detail::required<const uncompressed_type*>(arguments, "patch_data");
+	auto patch_indices          = detail::required<const index_type*>(arguments, "patch_indices");
+	auto num_patches            = detail::required<size_type>(arguments, "num_patches");
+	enqueue_launch(stream, launch_config, decompressed, compressed_input, dictionary_entries, length, num_dictionary_entries, caching,
+		patch_data, patch_indices, num_patches);
+}
+
+template <unsigned I, unsigned U, unsigned DI>
+const device_function_t kernel_t<I, U, DI>::get_device_function() const { return giddy_b200_patched_dictionary_kernel(I, U, DI); }
+
+} // namespace patched_dictionary
+
+/// Frame-of-Reference decode and compressed-indices patching in one pass (BASELINE.json configs[4], column A): the
+/// argument maps of decompression::frame_of_reference (reference frame_of_reference.cu:64-65,85-89) plus those of
+/// scatter::compressed_indices (compressed_indices_scatter.cu:54-55,76-88) minus "target", with
+/// OutputIndexSize = IndexSize and RunLengthSize = InputIndexSize.  Patch positions must be ascending.
+namespace patched_frame_of_reference {
+
+template <unsigned IndexSize, typename Uncompressed, typename Compressed, typename UnaryModelFunction, unsigned InputIndexSize>
+inline const void* kernel_address()
+{
+	return giddy_b200_patched_frame_of_reference_kernel(IndexSize, sizeof(Uncompressed), sizeof(Compressed),
+		(giddy_model_t) UnaryModelFunction::kind, UnaryModelFunction::index_size, InputIndexSize);
+}
+
+template <unsigned IndexSize, typename Uncompressed, typename Compressed, typename UnaryModelFunction, unsigned InputIndexSize = IndexSize>
+class launch_config_resolution_params_t final : public kernels::launch_config_resolution_params_t {
+public:
+	using parent = kernels::launch_config_resolution_params_t;
+	launch_config_resolution_params_t(device::properties_t device_properties_, ::std::size_t data_length, ::std::size_t segment_length,
+		optional<device_function::attributes_t> known_attributes = nullopt) :
+		parent(device_properties_, detail::attributes_or_query(known_attributes,
+			kernel_address<IndexSize, Uncompressed, Compressed, UnaryModelFunction, InputIndexSize>()))
+	{
+		// the same preconditions as the reference, frame_of_reference.cuh:99-104
+		if (segment_length == 0) { throw ::std::invalid_argument("The segment length must be a positive number"); }
+		if (segment_length % sizeof(native_word_t) != 0) {
+			throw ::std::invalid_argument("The segment length must be aligned with the GPU's native word size");
+		}
+		detail_patched::configure(*this, data_length, sizeof(Uncompressed));
+	}
+};
+
+template <unsigned IndexSize, typename Uncompressed, typename Compressed, typename UnaryModelFunction, unsigned InputIndexSize = IndexSize>
+class kernel_t : public cuda::registered::kernel_t {
+public:
+	GIDDY_WRAPPER_BOILERPLATE;
+	using index_type              = uint_t<IndexSize>;
+	using input_index_type        = uint_t<InputIndexSize>;
+	using input_size_type         = size_type_by_index_size<InputIndexSize>;
+	using model_coefficients_type = typename UnaryModelFunction::coefficients_type;
+
+	static ::std::string key()
+	{
+		return "decompression::composite::patched_frame_of_reference::kernel_t<" + detail::u(IndexSize) + ", " +
+			detail::type_name_of<Uncompressed>::get() + ", " + detail::type_name_of<Compressed>::get() + ", " +
+			detail::type_name_of<UnaryModelFunction>::get() + ", " + detail::u(InputIndexSize) + ">";
+	}
+
+	launch_configuration_t resolve_launch_configuration(
+		device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
+		::std::size_t length, ::std::size_t segment_length,
+		launch_configuration_limits_t limits = { nullopt, nullopt, nullopt }) const
+	{
+		launch_config_resolution_params_t<IndexSize, Uncompressed, Compressed, UnaryModelFunction, InputIndexSize> params(
+			device_properties, length, segment_length, optional<device_function::attributes_t>(kernel_function_attributes));
+		return kernels::resolve_launch_configuration(params, limits);
+	}
+
+	void enqueue_launch(stream::id_t stream, const launch_configuration_t& launch_config,
+		Uncompressed* decompressed, const Compressed* compressed_input, const model_coefficients_type* segment_model_coefficients,
+		index_type length, index_type segment_length,
+		const Uncompressed* data_to_scatter, const input_index_type* scatter_position_run_lengths,
+		const unsigned char* scatter_position_run_individual_offset_sizes, const index_type* scatter_position_run_baseline_values,
+		const input_index_type* scatter_position_run_offsets_start_pos, const unsigned char* scatter_position_offset_bytes,
+		const input_index_type* scatter_position_anchors, input_index_type anchoring_period, input_index_type num_scatter_position_runs,
+		input_size_type input_data_length) const
+	{
+		auto config = to_c(launch_config);
+		cuda::detail::throw_if_error(giddy_b200_patched_frame_of_reference_launch(stream, &config,
+			IndexSize, sizeof(Uncompressed), sizeof(Compressed), (giddy_model_t) UnaryModelFunction::kind, UnaryModelFunction::index_size, InputIndexSize,
+			decompressed, compressed_input, segment_model_coefficients, length, segment_length,
+			data_to_scatter, scatter_position_run_lengths, scatter_position_run_individual_offset_sizes, scatter_position_run_baseline_values,
+			scatter_position_run_offsets_start_pos, scatter_position_offset_bytes, scatter_position_anchors,
+			anchoring_period, num_scatter_position_runs, input_data_length));
+	}
+};
+
+template <unsigned I, typename U, typename C, typename M, unsigned II>
+launch_configuration_t kernel_t<I, U, C, M, II>::resolve_launch_configuration(
+	device::properties_t device_properties, device_function::attributes_t kernel_function_attributes,
+	arguments_type extra_arguments, launch_configuration_limits_t limits) const
+{
+	auto length         = detail::required<::std::size_t>(extra_arguments, "length");
+	auto segment_length = detail::required<::std::size_t>(extra_arguments, "segment_length");
+	return resolve_launch_configuration(device_properties, kernel_function_attributes, length, segment_length, limits);
+}
+
+template <unsigned I, typename U, typename C, typename M, unsigned II>
+void kernel_t<I, U, C, M, II>::enqueue_launch(stream::id_t stream, const launch_configuration_t& launch_config, arguments_type arguments) const
+{
+	auto decompressed               = detail::required<U*>(arguments, "decompressed");
+	auto compressed_input           = detail::required<const C*>(arguments, "compressed_input");
+	auto segment_model_coefficients = detail::required<const model_coefficients_type*>(arguments, "segment_model_coefficients");
+	auto length                     = detail::required<index_type>(arguments, "length");
+	auto segment_length             = detail::required<index_type>(arguments, "segment_length");
+	auto data_to_scatter                              = detail::required<const U*>(arguments, "data_to_scatter");
+	auto scatter_position_run_lengths                 = detail::required<const input_index_type*>(arguments, "scatter_position_run_lengths");
+	auto scatter_position_run_individual_offset_sizes = detail::required<const unsigned char*>(arguments, "scatter_position_run_individual_offset_sizes");
+	auto scatter_position_run_baseline_values         = detail::required<const index_type*>(arguments, "scatter_position_run_baseline_values");
+	auto scatter_position_run_offsets_start_pos       = detail::required<const input_index_type*>(arguments, "scatter_position_run_offsets_start_pos");
+	auto scatter_position_offset_bytes                = detail::required<const unsigned char*>(arguments, "scatter_position_offset_bytes");
+	auto scatter_position_anchors                     = detail::required<const input_index_type*>(arguments, "scatter_position_anchors");
+	auto anchoring_period                             = detail::required<input_index_type>(arguments, "anchoring_period");
+	auto num_scatter_position_runs                    = detail::required<input_index_type>(arguments, "num_scatter_position_runs");
+	auto input_data_length                            = detail::required<input_size_type>(arguments, "input_data_length");
+	enqueue_launch(stream, launch_config, decompressed, compressed_input, segment_model_coefficients, length, segment_length,
+		data_to_scatter, scatter_position_run_lengths, scatter_position_run_individual_offset_sizes, scatter_position_run_baseline_values,
+		scatter_position_run_offsets_start_pos, scatter_position_offset_bytes, scatter_position_anchors,
+		anchoring_period, num_scatter_position_runs, input_data_length);
+}
+
+template <unsigned I, typename U, typename C, typename M, unsigned II>
+const device_function_t kernel_t<I, U, C, M, II>::get_device_function() const { return kernel_address<I, U, C, M, II>(); }
+
+} // namespace patched_frame_of_reference
 } // namespace composite
 
 // =================================================================================================

@@ -349,6 +349,44 @@ GIDDY_API giddy_status_t giddy_b200_delta_of_discard_zero_bytes_variable_launch(
 	const void* anchor_values, uint64_t segment_length, uint64_t length,
 	unsigned min_represented_element_size, unsigned bits_per_element_size);
 
+/* Patched decoders: a decoder and the a-posteriori patching kernel which the reference would run after it
+ * (README.md:55-60), in one pass.  A patch is stored right after the tile which contains it, while that tile is
+ * still in L2, instead of costing a read-modify-write of a 32-byte HBM sector in a second pass.
+ * Both need the patch positions in ASCENDING order. */
+
+/* dictionary::decompress<IndexSize, UncompressedSize, DictionaryIndexSize> (src/kernels/decompression/dictionary.cuh:61-75)
+ * then scatter::scatter<IndexSize, UncompressedSize, IndexSize> (src/kernels/data_layout/scatter.cuh:26-46) onto its output:
+ *   decompressed[i] = dictionary_entries[compressed_input[i]];  decompressed[patch_indices[k]] = patch_data[k], k < num_patches */
+GIDDY_API const void* giddy_b200_patched_dictionary_kernel(
+	unsigned index_size, unsigned uncompressed_size, unsigned dictionary_index_size);
+GIDDY_API giddy_status_t giddy_b200_patched_dictionary_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned index_size, unsigned uncompressed_size, unsigned dictionary_index_size,
+	void* decompressed, const void* compressed_input, const void* dictionary_entries,
+	uint64_t length, uint64_t num_dictionary_entries, int cache_dictionary_in_shared_memory,
+	const void* patch_data, const void* patch_indices, uint64_t num_patches);
+
+/* frame_of_reference::decompress<IndexSize, Uncompressed, Compressed, Model> (src/kernels/decompression/frame_of_reference.cuh:35-80)
+ * then scatter::compressed_indices::scatter<IndexSize, Uncompressed, InputIndexSize, InputIndexSize>
+ * (src/kernels/data_layout/compressed_indices_scatter.cuh:219-271) onto its output.  The patch arguments are that kernel's. */
+GIDDY_API const void* giddy_b200_patched_frame_of_reference_kernel(
+	unsigned index_size, unsigned uncompressed_size, unsigned compressed_size,
+	giddy_model_t model, unsigned model_index_size, unsigned input_index_size);
+GIDDY_API giddy_status_t giddy_b200_patched_frame_of_reference_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned index_size, unsigned uncompressed_size, unsigned compressed_size,
+	giddy_model_t model, unsigned model_index_size, unsigned input_index_size,
+	void* decompressed, const void* compressed_input, const void* segment_model_coefficients,
+	uint64_t length, uint64_t segment_length,
+	const void* data_to_scatter,
+	const void* scatter_position_run_lengths,
+	const void* scatter_position_run_individual_offset_sizes,
+	const void* scatter_position_run_baseline_values,
+	const void* scatter_position_run_offsets_start_positions,
+	const void* scatter_position_offset_bytes,
+	const void* scatter_position_anchors,
+	uint64_t anchoring_period, uint64_t num_scatter_position_runs, uint64_t data_length);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -9,7 +9,8 @@ using namespace giddy::abi;
 namespace {
 
 using delta_launcher_t = giddy_status_t (*)(void*, const giddy_launch_config_t*, void*, const void*, const void*, uint64_t, uint64_t);
-struct delta_entry_t { unsigned I, U, C; const void* kernel; delta_launcher_t launch; };
+using delta_long_launcher_t = giddy_status_t (*)(void*, const giddy_launch_config_t*, void*, const void*, const void*, uint64_t, uint64_t, void*);
+struct delta_entry_t { unsigned I, U, C; const void* kernel; delta_launcher_t launch; delta_long_launcher_t launch_long; };
 
 template <unsigned I, unsigned U, unsigned C>
 giddy_status_t delta_launch(void* stream, const giddy_launch_config_t* cfg, void* out, const void* in, const void* anchors, uint64_t n, uint64_t L)
@@ -18,7 +19,15 @@ giddy_status_t delta_launch(void* stream, const giddy_launch_config_t* cfg, void
 		static_cast<uint_t<U>*>(out), static_cast<const uint_t<C>*>(in), static_cast<const uint_t<U>*>(anchors),
 		(size_type<I>) n, (size_type<I>) L);
 }
-#define DELTA_ENTRY(I, U, C) { I, U, C, reinterpret_cast<const void*>(&kernels::delta_decompress<I, U, C>), &delta_launch<I, U, C> }
+template <unsigned I, unsigned U, unsigned C>
+giddy_status_t delta_long_launch(void* stream, const giddy_launch_config_t* cfg, void* out, const void* in, const void* anchors, uint64_t n, uint64_t L,
+	void* workspace)
+{
+	return launch(kernels::delta_decompress_long_segments<I, U, C>, stream, cfg,
+		static_cast<uint_t<U>*>(out), static_cast<const uint_t<C>*>(in), static_cast<const uint_t<U>*>(anchors),
+		(size_type<I>) n, (size_type<I>) L, workspace);
+}
+#define DELTA_ENTRY(I, U, C) { I, U, C, reinterpret_cast<const void*>(&kernels::delta_decompress<I, U, C>), &delta_launch<I, U, C>, &delta_long_launch<I, U, C> }
 #define DELTA_ENTRIES(I) DELTA_ENTRY(I, 2, 1), DELTA_ENTRY(I, 4, 1), DELTA_ENTRY(I, 4, 2), DELTA_ENTRY(I, 8, 1), DELTA_ENTRY(I, 8, 2), DELTA_ENTRY(I, 8, 4)
 
 const delta_entry_t delta_table[] = { DELTA_ENTRIES(4), DELTA_ENTRIES(8) };
@@ -46,5 +55,29 @@ extern "C" giddy_status_t giddy_b200_delta_launch(
 	if (!check_launch(config, e ? e->kernel : nullptr, status)) { return status; }
 	if (segment_length == 0) { return fail(GIDDY_INVALID_ARGUMENT, "The segment length must be a positive number"); }
 	if (length == 0) { return GIDDY_SUCCESS; }
-	return e->launch(stream, config, decompressed, compressed_input, anchor_values, length, segment_length);
+	if (!GIDDY_DELTA_USES_LOOK_BACK(length, segment_length, U)) {
+		return e->launch(stream, config, decompressed, compressed_input, anchor_values, length, segment_length);
+	}
+	// Few, long segments: tiles with decoupled look-back (kernels/delta.cuh).  The tile descriptors live in a
+	// workspace taken from the stream-ordered allocator for the duration of this launch -- allocation, zeroing,
+	// kernel and release are all enqueued on the caller's stream; nothing synchronises and nothing is kept.
+	const unsigned threads = config->block_dimensions[0];
+	if (threads % 32 != 0 || threads == 0) { return fail(GIDDY_INVALID_ARGUMENT, "blocks must be made of whole warps"); }
+	const unsigned E = 16 / U;
+	const bool vectorizable = reinterpret_cast<uintptr_t>(decompressed) % 16 == 0 &&
+		reinterpret_cast<uintptr_t>(compressed_input) % (E * C) == 0 && segment_length % E == 0;
+	const uint64_t tile_elements = (uint64_t) threads * GIDDY_DELTA_ROWS_PER_STEP * (vectorizable ? E : 1);
+	const uint64_t num_segments = (length + segment_length - 1) / segment_length;
+	const uint64_t num_tiles = num_segments * ((segment_length + tile_elements - 1) / tile_elements); // an upper bound
+	const size_t workspace_bytes = 32 + (size_t) num_tiles * 32;
+	void* workspace = nullptr;
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	cudaError_t error = cudaMallocAsync(&workspace, workspace_bytes, s);
+	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocAsync (Delta look-back workspace)"); }
+	error = cudaMemsetAsync(workspace, 0, workspace_bytes, s);
+	if (error != cudaSuccess) { cudaFreeAsync(workspace, s); return fail_cuda(error, "cudaMemsetAsync (Delta look-back workspace)"); }
+	status = e->launch_long(stream, config, decompressed, compressed_input, anchor_values, length, segment_length, workspace);
+	error = cudaFreeAsync(workspace, s);
+	if (status == GIDDY_SUCCESS && error != cudaSuccess) { return fail_cuda(error, "cudaFreeAsync (Delta look-back workspace)"); }
+	return status;
 }

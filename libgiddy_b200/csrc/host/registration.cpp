@@ -124,6 +124,24 @@ void register_all_wrappers()
 		kernel_t<4, 8, 2, 4>::registerInSubclassFactory(); kernel_t<4, 4, 2, 4>::registerInSubclassFactory();
 		kernel_t<8, 8, 4, 4>::registerInSubclassFactory();
 	}
+	{
+		using namespace decompression::composite::patched_dictionary;
+		kernel_t<4, 1, 1>::registerInSubclassFactory(); kernel_t<4, 2, 1>::registerInSubclassFactory();
+		kernel_t<4, 4, 1>::registerInSubclassFactory(); kernel_t<4, 8, 1>::registerInSubclassFactory();
+		kernel_t<4, 2, 2>::registerInSubclassFactory(); kernel_t<4, 4, 2>::registerInSubclassFactory();
+		kernel_t<4, 8, 2>::registerInSubclassFactory(); kernel_t<4, 8, 4>::registerInSubclassFactory();
+		kernel_t<8, 8, 1>::registerInSubclassFactory(); kernel_t<8, 4, 2>::registerInSubclassFactory();
+	}
+	{
+		using namespace decompression::composite::patched_frame_of_reference;
+		kernel_t<4, int16_t, int8_t,  models::linear<4, int32_t>, 4>::registerInSubclassFactory();
+		kernel_t<4, int32_t, int8_t,  models::linear<4, int32_t>, 4>::registerInSubclassFactory();
+		kernel_t<4, int32_t, int16_t, models::linear<4, int32_t>, 4>::registerInSubclassFactory();
+		kernel_t<8, int32_t, int16_t, models::linear<8, int32_t>, 8>::registerInSubclassFactory();
+		kernel_t<4, int16_t, int8_t,  models::constant<4, int32_t>, 4>::registerInSubclassFactory();
+		kernel_t<4, int32_t, int8_t,  models::constant<4, int32_t>, 4>::registerInSubclassFactory();
+		kernel_t<4, int32_t, int16_t, models::constant<4, int32_t>, 4>::registerInSubclassFactory();
+	}
 }
 
 } // namespace host

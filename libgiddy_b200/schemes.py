@@ -276,6 +276,71 @@ def delta_of_discard_zero_bytes_variable(decompressed, compressed_data, packed_e
                 stream, limits)
 
 
+def patched_dictionary_key(index_size, uncompressed_size, dictionary_index_size):
+    return "decompression::composite::patched_dictionary::kernel_t<%du, %du, %du>" % (index_size, uncompressed_size, dictionary_index_size)
+
+
+def patched_dictionary(decompressed, compressed_input, dictionary_entries, length, num_dictionary_entries,
+                       patch_data, patch_indices, num_patches, *,
+                       uncompressed_size, dictionary_index_size, index_size=4, cache_in_shared_memory=None,
+                       stream=None, limits=None, library=None):
+    """Extension: Dictionary decode + naive patching (scatter) in one pass; patch_indices ascending."""
+    _check_size(decompressed, uncompressed_size, "decompressed")
+    _check_size(compressed_input, dictionary_index_size, "compressed_input")
+    _check_size(patch_data, uncompressed_size, "patch_data")
+    _check_size(patch_indices, index_size, "patch_indices")
+    resolve = {"num_dictionary_entries": N.size_t(num_dictionary_entries), "data_length": N.size_t(length)}
+    if cache_in_shared_memory is not None:
+        resolve["cache_input_data_in_shared_mem"] = N.boolean(cache_in_shared_memory)
+    size = N.size_type_by_index_size(index_size)
+    return _run(library, patched_dictionary_key(index_size, uncompressed_size, dictionary_index_size), resolve,
+                {"decompressed": N.ptr(decompressed, _UTAG[uncompressed_size]),
+                 "compressed_input": N.cptr(compressed_input, _UTAG[dictionary_index_size]),
+                 "dictionary_entries": N.cptr(dictionary_entries, _UTAG[uncompressed_size]),
+                 "length": size(length),
+                 "num_dictionary_entries": N.size_type_by_index_size(dictionary_index_size)(num_dictionary_entries),
+                 "patch_data": N.cptr(patch_data, _UTAG[uncompressed_size]),
+                 "patch_indices": N.cptr(patch_indices, _UTAG[index_size]),
+                 "num_patches": size(num_patches)},
+                stream, limits)
+
+
+def patched_frame_of_reference_key(index_size, uncompressed_size, compressed_size, model="constant", model_index_size=4, input_index_size=None):
+    return "decompression::composite::patched_frame_of_reference::kernel_t<%du, %s, %s, %s, %du>" % (
+        index_size, _SIGNED_NAMES[uncompressed_size], _SIGNED_NAMES[compressed_size], model_type_name(model, model_index_size),
+        input_index_size or index_size)
+
+
+def patched_frame_of_reference(decompressed, compressed_input, segment_model_coefficients, length, segment_length,
+                               data_to_scatter, run_lengths, run_individual_offset_sizes, run_baseline_values,
+                               run_offsets_start_pos, offset_bytes, anchors, anchoring_period, num_runs, input_data_length, *,
+                               uncompressed_size, compressed_size, model="constant", index_size=4, model_index_size=4,
+                               input_index_size=None, stream=None, limits=None, library=None):
+    """Extension: Frame-of-Reference decode + compressed-indices patching in one pass; patch positions ascending."""
+    input_index_size = input_index_size or index_size
+    _check_size(decompressed, uncompressed_size, "decompressed")
+    _check_size(compressed_input, compressed_size, "compressed_input")
+    _check_size(data_to_scatter, uncompressed_size, "data_to_scatter")
+    dim = 2 if model == "linear" else 1
+    index, ii = N.uint_of_size(index_size), N.uint_of_size(input_index_size)
+    return _run(library, patched_frame_of_reference_key(index_size, uncompressed_size, compressed_size, model, model_index_size, input_index_size),
+                {"length": N.size_t(length), "segment_length": N.size_t(segment_length)},
+                {"decompressed": N.ptr(decompressed, _ITAG[uncompressed_size]),
+                 "compressed_input": N.cptr(compressed_input, _ITAG[compressed_size]),
+                 "segment_model_coefficients": N.cptr(segment_model_coefficients, "array_i32_%d" % dim),
+                 "length": index(length), "segment_length": index(segment_length),
+                 "data_to_scatter": N.cptr(data_to_scatter, _ITAG[uncompressed_size]),
+                 "scatter_position_run_lengths": N.cptr(run_lengths, _UTAG[input_index_size]),
+                 "scatter_position_run_individual_offset_sizes": N.cptr(run_individual_offset_sizes, "u8"),
+                 "scatter_position_run_baseline_values": N.cptr(run_baseline_values, _UTAG[index_size]),
+                 "scatter_position_run_offsets_start_pos": N.cptr(run_offsets_start_pos, _UTAG[input_index_size]),
+                 "scatter_position_offset_bytes": N.cptr(offset_bytes, "u8"),
+                 "scatter_position_anchors": N.cptr(anchors, _UTAG[input_index_size]),
+                 "anchoring_period": ii(anchoring_period), "num_scatter_position_runs": ii(num_runs),
+                 "input_data_length": N.size_type_by_index_size(input_index_size)(input_data_length)},
+                stream, limits)
+
+
 def incidence_bitmaps(decompressed, bitmaps, dictionary_entries, length, bitmap_length, num_bitmaps, *,
                       uncompressed_size, alignment_in_ints=2, use_dictionary=True, index_size=4,
                       stream=None, limits=None, library=None):

@@ -318,6 +318,72 @@ def ci_scatter_case(seed, target_length, p, U, OI, II, A, max_run_length=64, wid
                 initial_output=target)
 
 
+def patched_dictionary_case(seed, n, U, DI, num_entries, p, I=4, cache=None, clustered=False):
+    """Extension: Dictionary + naive patches in one pass; expected = the oracle's dictionary decode, then its scatter."""
+    r = rng(12, seed, n, U, DI, num_entries, p)
+    entries = random_uint(r, U, num_entries)
+    indices = r.integers(0, num_entries, n, dtype=np.uint64).astype(UINT[DI])
+    if clustered and p:  # all patches inside a few tiles: more patches than threads in a tile
+        start = int(r.integers(0, max(n - 2 * p, 1)))
+        positions = start + np.sort(r.choice(min(2 * p, n - start), p, replace=False))
+    else:
+        positions = np.sort(r.choice(n, p, replace=False))
+    positions = positions.astype(UINT[I])
+    data = random_uint(r, U, p)
+    expected = O.scatter(O.dictionary(indices, entries, n), data, positions)
+
+    def launch(out, t, library, limits):
+        S.patched_dictionary(out, t["compressed_input"], t["dictionary_entries"], n, num_entries, t["patch_data"], t["patch_indices"], p,
+                             uncompressed_size=U, dictionary_index_size=DI, index_size=I, cache_in_shared_memory=cache,
+                             library=library, limits=limits)
+    # keep the device buffers non-empty when there are no patches
+    inputs = {"compressed_input": indices, "dictionary_entries": entries,
+              "patch_data": data if p else np.zeros(1, UINT[U]), "patch_indices": positions if p else np.zeros(1, UINT[I])}
+    return Case("patched-dict-I%d-U%d-DI%d-D%d-n%d-p%d%s" % (I, U, DI, num_entries, n, p, "-clustered" if clustered else ""),
+                "patched_dictionary", inputs, dict(n=n, p=p), expected, launch, ref_ok=False)
+
+
+def patched_for_case(seed, n, L, U, C, model, p, A, I=4, MI=4, max_run_length=64, widths=(8, 16, 32), clustered=False):
+    """Extension: FOR + compressed-indices patches in one pass; expected = the oracle's FOR decode, then its ci-scatter."""
+    r = rng(13, seed, n, L, U, C, p, A)
+    num_segments = E.num_segments(n, L)
+    dim = 2 if model == "linear" else 1
+    coefficients = r.integers(-(1 << 30), 1 << 30, (num_segments, dim), dtype=np.int64).astype(np.int32)
+    if model == "linear":
+        coefficients[:, 1] = r.integers(-1000, 1000, num_segments)
+    compressed = r.integers(-(1 << (8 * C - 1)), 1 << (8 * C - 1), n, dtype=np.int64).astype(INT[C])
+    if clustered and p:
+        start = int(r.integers(0, max(n - 2 * p, 1)))
+        positions = start + np.sort(r.choice(min(2 * p, n - start), p, replace=False))
+    else:
+        positions = np.sort(r.choice(n, p, replace=False))
+    data = random_uint(r, U, p)
+    enc = E.compressed_indices_encode(positions, A, I, I, max_run_length, widths)
+    decoded = O.frame_of_reference(compressed, coefficients, n, L, U, model, MI)
+    if p:
+        expected = O.compressed_indices_scatter(decoded.view(UINT[U]).copy(), data, enc["scatter_position_run_lengths"],
+                                                enc["scatter_position_run_individual_offset_sizes"], enc["scatter_position_run_baseline_values"],
+                                                enc["scatter_position_run_offsets_start_pos"], enc["scatter_position_offset_bytes"],
+                                                enc["scatter_position_anchors"], A).view(decoded.dtype)
+    else:
+        expected = decoded
+    num_runs = len(enc["scatter_position_run_lengths"])
+    inputs = {k: (v if len(v) else np.zeros(1, v.dtype)) for k, v in enc.items()}
+    inputs["scatter_position_offset_bytes"] = np.concatenate((enc["scatter_position_offset_bytes"], np.zeros(8, np.uint8)))
+    inputs.update(compressed_input=compressed, segment_model_coefficients=coefficients,
+                  data_to_scatter=(data if p else np.zeros(1, UINT[U])).view(INT[U]))
+
+    def launch(out, t, library, limits):
+        S.patched_frame_of_reference(out, t["compressed_input"], t["segment_model_coefficients"], n, L,
+                                     t["data_to_scatter"], t["scatter_position_run_lengths"], t["scatter_position_run_individual_offset_sizes"],
+                                     t["scatter_position_run_baseline_values"], t["scatter_position_run_offsets_start_pos"],
+                                     t["scatter_position_offset_bytes"], t["scatter_position_anchors"], A, num_runs, p,
+                                     uncompressed_size=U, compressed_size=C, model=model, index_size=I, model_index_size=MI,
+                                     library=library, limits=limits)
+    return Case("patched-for-%s-I%d-U%d-C%d-n%d-L%d-p%d-A%d-r%d%s" % (model, I, U, C, n, L, p, A, max_run_length, "-clustered" if clustered else ""),
+                "patched_frame_of_reference", inputs, dict(n=n, L=L, p=p, A=A), expected, launch, ref_ok=False)
+
+
 # ---- the case list ---------------------------------------------------------------------------------
 
 def all_cases():
@@ -363,6 +429,14 @@ def all_cases():
     cases.append(delta_case(3, 10000, 24, 4, 2))                          # segments shorter than a row
     cases.append(delta_case(4, 300000, 100000, 8, 4))                     # long segments
     cases.append(delta_case(5, 1 << 20, 1024, 8, 4))
+    # few, long segments: the decoupled look-back path (tiles of a segment scanned by different CTAs)
+    cases.append(delta_case(6, 1 << 20, 1 << 20, 8, 4))                   # a single segment: a plain prefix sum over the column
+    cases.append(delta_case(7, 4 << 16, 1 << 16, 4, 2))                   # the reference is defined here too
+    cases.append(delta_case(8, 500000 + 7, 200000, 8, 4))                 # ragged last segment
+    cases.append(delta_case(9, 600000, 131071, 4, 1))                     # L odd: element-wise tiles
+    cases.append(delta_case(10, 1 << 20, 1 << 18, 2, 1))
+    cases.append(delta_case(11, 3 << 18, 1 << 18, 8, 1, I=8))
+    cases.append(delta_case(12, (1 << 22) + 5, 1 << 21, 8, 2))
     # Dictionary (20 keys)
     for I in (4, 8):
         for (U, DI) in [(1, 1), (2, 1), (2, 2), (4, 1), (4, 2), (4, 4), (8, 1), (8, 2), (8, 4), (8, 8)]:
@@ -403,6 +477,29 @@ def all_cases():
     cases.append(dzbv_delta_case(3, 4000 + 5, 16, 8, 4, 4, 2, 1))         # tiny segments
     cases.append(dzbv_delta_case(4, 33000, 1024, 8, 4, 4, 4, 0))          # 4-bit fields
     cases.append(dzbv_delta_case(5, 1 << 20, 1024, 8, 4, 4, 2, 1))
+    # Extension: Dictionary + naive patches, fused (10 keys)
+    for (I, U, DI) in [(4, 1, 1), (4, 2, 1), (4, 4, 1), (4, 8, 1), (4, 2, 2), (4, 4, 2), (4, 8, 2), (4, 8, 4), (8, 8, 1), (8, 4, 2)]:
+        cases.append(patched_dictionary_case(0, 100000 + 11, U, DI, min(1 << (8 * DI), 1000), 1000, I))
+    cases.append(patched_dictionary_case(1, 1 << 20, 8, 1, 256, 10485, cache=True))      # 1 % exceptions (BASELINE configs[2] in small)
+    cases.append(patched_dictionary_case(2, 1 << 20, 8, 1, 256, 10485, cache=False))
+    cases.append(patched_dictionary_case(3, 300000, 8, 1, 256, 0))                       # no patches at all
+    cases.append(patched_dictionary_case(4, 300000 + 1, 8, 1, 256, 1))                   # a single patch; one trailing element
+    cases.append(patched_dictionary_case(5, 200000, 4, 1, 200, 3000, clustered=True))    # more patches in a tile than the CTA has threads
+    cases.append(patched_dictionary_case(6, 50000, 2, 2, 5000, 50000))                   # every element patched
+    cases.append(patched_dictionary_case(7, 9, 8, 1, 3, 2))
+    cases.append(patched_dictionary_case(8, 1 << 22, 4, 1, 256, 200000))
+    # Extension: Frame of Reference + compressed-indices patches, fused (7 keys)
+    for (I, U, C, model, MI) in [(4, 2, 1, "linear", 4), (4, 4, 1, "linear", 4), (4, 4, 2, "linear", 4), (8, 4, 2, "linear", 8),
+                                 (4, 2, 1, "constant", 4), (4, 4, 1, "constant", 4), (4, 4, 2, "constant", 4)]:
+        cases.append(patched_for_case(0, 40 * 2048, 2048, U, C, model, 2000, 256, I, MI))
+    cases.append(patched_for_case(1, 1 << 20, 1024, 4, 2, "linear", 10485, 1024))                   # BASELINE configs[4] column A in small
+    cases.append(patched_for_case(2, 100000 + 13, 1020, 4, 2, "linear", 3000, 1000, max_run_length=7))   # ragged; many short runs
+    cases.append(patched_for_case(3, 300000, 4096, 4, 2, "constant", 0, 1024))                      # no patches
+    cases.append(patched_for_case(4, 300000, 4096, 4, 2, "constant", 1, 1024))
+    cases.append(patched_for_case(5, 200000, 1024, 4, 1, "linear", 5000, 4096, max_run_length=3000, clustered=True))  # runs longer than the window
+    cases.append(patched_for_case(6, 60000, 1024, 2, 1, "constant", 60000, 1024, max_run_length=1))  # every element patched, one-patch runs
+    cases.append(patched_for_case(7, 1 << 22, 4096, 4, 2, "constant", 150000, 100000, max_run_length=500))  # long anchoring period
+    cases.append(patched_for_case(8, 1 << 21, 1024, 4, 2, "linear", 30000, 16, max_run_length=16))   # tiny anchoring period
     # Incidence bitmaps (5 keys)
     for (U, use_dictionary) in [(1, True), (2, True), (4, True), (8, True), (1, False)]:
         cases.append(bitmaps_case(0, 64 * 1024, U, 16, use_dictionary))

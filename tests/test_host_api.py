@@ -23,7 +23,7 @@ def resolve(library, key, arguments, **kwargs):
 def test_library_exports_every_declared_symbol(library):
     header = open(os.path.join(ROOT, "include", "giddy_b200.h")).read()
     declared = set(re.findall(r"GIDDY_API[^;(]*?\b(giddy_\w+)\s*\(", header))
-    assert len(declared) == 38
+    assert len(declared) == 42
     exported = subprocess.run(["nm", "-D", "--defined-only", library.path], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r" T (giddy_\w+)", exported))
     assert declared <= exported, declared - exported
@@ -70,8 +70,15 @@ def test_factory_holds_the_reference_key_set(library):
     # every reference key, plus nothing but this library's documented extensions
     assert set(expected) <= set(registered)
     extensions = sorted(set(registered) - set(expected))
-    assert extensions == sorted("decompression::composite::delta_of_discard_zero_bytes_variable_width::kernel_t<%du, %du, %du, %du>" % t
-                                for t in [(4, 8, 4, 4), (4, 8, 4, 8), (4, 8, 2, 4), (4, 4, 2, 4), (8, 8, 4, 4)])
+    import libgiddy_b200.schemes as S
+    documented = ["decompression::composite::delta_of_discard_zero_bytes_variable_width::kernel_t<%du, %du, %du, %du>" % t
+                  for t in [(4, 8, 4, 4), (4, 8, 4, 8), (4, 8, 2, 4), (4, 4, 2, 4), (8, 8, 4, 4)]]
+    documented += [S.patched_dictionary_key(*t) for t in [(4, 1, 1), (4, 2, 1), (4, 4, 1), (4, 8, 1), (4, 2, 2), (4, 4, 2), (4, 8, 2),
+                                                          (4, 8, 4), (8, 8, 1), (8, 4, 2)]]
+    documented += [S.patched_frame_of_reference_key(*t) for t in [(4, 2, 1, "linear", 4, 4), (4, 4, 1, "linear", 4, 4), (4, 4, 2, "linear", 4, 4),
+                                                                  (8, 4, 2, "linear", 8, 8), (4, 2, 1, "constant", 4, 4),
+                                                                  (4, 4, 1, "constant", 4, 4), (4, 4, 2, "constant", 4, 4)]]
+    assert extensions == sorted(documented)
     # the key the reference's own example uses (examples/src/modes_of_use/factory_provided_type_erased_wrapper.cu:15-16)
     example = "decompression::frame_of_reference::kernel_t<4u, int, short, cuda::functors::unary::parametric_model::constant<4u, int> >"
     assert library.can_produce(example)
