@@ -45,6 +45,9 @@ def workloads(log2_n):
     w.append(("Delta u32<-u8 one segment (look-back)", lambda: cases.delta_case(1, n, n, 4, 1)))
     w.append(("cfg3 Dictionary u64<-u8 D=256", lambda: cases.dictionary_case(1, n // 2, 8, 1, 256)))
     w.append(("Dictionary u32<-u16 D=60000 (L2 gather)", lambda: cases.dictionary_case(1, n, 4, 2, 60000, cache=False)))
+    w.append(("Dictionary u32<-u16 D=60000 (shared-memory head, persistent)", lambda: cases.dictionary_case(1, n, 4, 2, 60000, cache=True)))
+    w.append(("Dictionary u32<-u16 D=40000 (shared memory, persistent)", lambda: cases.dictionary_case(1, n, 4, 2, 40000, cache=True)))
+    w.append(("Dictionary u32<-u16 D=60000 (default policy)", lambda: cases.dictionary_case(1, n, 4, 2, 60000)))
     w.append(("DZB-fixed u32<-u16", lambda: cases.dzbf_case(1, n, 4, 2)))
     w.append(("DZB-fixed u64<-u8", lambda: cases.dzbf_case(1, n // 2, 8, 1)))
     w.append(("cfg4 DZB-variable u32 2-bit sizes L=1024", lambda: cases.dzbv_case(1, n, 1024, 4, 4, 2, 1)))

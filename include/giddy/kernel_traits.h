@@ -39,11 +39,21 @@
  * segment could not fill the GPU) are decoded tile by tile with decoupled look-back instead: CTAs of this many threads,
  * tiles of threads * rows * (16 / U) elements, persistent CTAs fed by a ticket counter. */
 #define GIDDY_DELTA_ROWS_PER_STEP 4
+#ifndef GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS
 #define GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS 256
-#define GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR 8
-#define GIDDY_DELTA_TILE_ELEMENTS(U, threads) ((threads) * GIDDY_DELTA_ROWS_PER_STEP * (16 / (U)))
+#endif
+#ifndef GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR
+#define GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR 3
+#endif
+#ifndef GIDDY_DELTA_LOOK_BACK_ROWS
+#define GIDDY_DELTA_LOOK_BACK_ROWS 12
+#endif
+#ifndef GIDDY_DELTA_LOOK_BACK_WINDOW
+#define GIDDY_DELTA_LOOK_BACK_WINDOW 4             /* descriptors inspected per lane per look-back round */
+#endif
+#define GIDDY_DELTA_TILE_ELEMENTS(U, threads) ((threads) * GIDDY_DELTA_LOOK_BACK_ROWS * (16 / (U)))
 #define GIDDY_DELTA_USES_LOOK_BACK(length, segment_length, U) \
-	((segment_length) >= 4 * GIDDY_DELTA_TILE_ELEMENTS(U, GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS) && \
+	((segment_length) >= 2 * GIDDY_DELTA_TILE_ELEMENTS(U, GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS) && \
 	 ((length) + (segment_length) - 1) / (segment_length) < 8192)
 
 /* Patched decoders (decode + patches in one pass): every warp owns a contiguous range of warp tiles (32 x

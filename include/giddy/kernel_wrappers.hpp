@@ -558,6 +558,8 @@ namespace dictionary {
 
 /// Dictionaries up to this size are, by default, staged in shared memory by every CTA
 enum : unsigned { max_default_cached_dictionary_bytes = 32 * 1024 };
+/// ... and larger ones by a persistent grid, if at least this much shared memory is to be had for them
+enum : unsigned { min_large_cached_dictionary_bytes = 96 * 1024 };
 
 template <unsigned IndexSize, unsigned UncompressedSize, unsigned DictionaryIndexSize>
 class launch_config_resolution_params_t final : public kernels::launch_config_resolution_params_t {
@@ -570,17 +572,31 @@ public:
 		parent(device_properties_, detail::attributes_or_query(known_attributes, giddy_b200_dictionary_kernel(IndexSize, UncompressedSize, DictionaryIndexSize)), dynamic_shared_mem_limit)
 	{
 		const ::std::size_t dictionary_bytes = input_data_length * UncompressedSize;
+		const ::std::size_t output_bytes = num_indices * UncompressedSize;
 		// The reference never caches by default ("seems to mostly hurt us", gather.cuh:202-205 -- its caching
-		// path is commented out).  Here a small dictionary is read from HBM once per CTA and then served from
-		// shared memory, provided the column is long enough to amortise that.
-		const bool worthwhile = dictionary_bytes <= max_default_cached_dictionary_bytes &&
-			dictionary_bytes <= available_dynamic_shared_memory_per_block && num_indices * UncompressedSize >= 64 * dictionary_bytes;
-		const bool cache = cache_input_data_in_shared_memory_override.value_or(worthwhile);
+		// path is commented out).  Here
+		//  * a small dictionary is read once per CTA and then served from shared memory, provided the column is long
+		//    enough to amortise that;
+		//  * a large one (random lookups into it run at about half of HBM speed through L1/L2) is worth a persistent
+		//    grid of one big CTA per multiprocessor, each holding the dictionary -- or as much of its head as fits -- in
+		//    up to 227 KiB of shared memory, once the column is ~1000 times the dictionary's size.
+		const bool small_worthwhile = dictionary_bytes <= max_default_cached_dictionary_bytes &&
+			dictionary_bytes <= available_dynamic_shared_memory_per_block && output_bytes >= 64 * dictionary_bytes;
+		const bool large_worthwhile = dictionary_bytes > max_default_cached_dictionary_bytes &&
+			available_dynamic_shared_memory_per_block >= min_large_cached_dictionary_bytes && output_bytes / 1024 >= dictionary_bytes;
+		const bool cache = cache_input_data_in_shared_memory_override.value_or(small_worthwhile || large_worthwhile);
 		grid_construction_resolution   = thread;
 		length                         = num_indices;
+		quanta.threads_in_block        = warp_size;
+		if (cache && dictionary_bytes > max_default_cached_dictionary_bytes) {
+			const ::std::size_t room = (available_dynamic_shared_memory_per_block / 16) * 16;
+			dynamic_shared_memory_requirement.per_block = (shared_memory_size_t) ::std::min(dictionary_bytes, room);
+			serialization_option       = auto_maximized;
+			keep_gpu_busy_factor       = 8; // x 4 schedulers / 32 warps: one CTA of 1024 threads per multiprocessor
+			return;
+		}
 		serialization_option           = runtime_specified_factor;
 		default_serialization_factor   = (16 / UncompressedSize) * GIDDY_ELEMENTWISE_UNROLL;
-		quanta.threads_in_block        = warp_size;
 		upper_limits.threads_in_block  = GIDDY_ELEMENTWISE_BLOCK_THREADS;
 		if (cache) { dynamic_shared_memory_requirement.per_block = (shared_memory_size_t) dictionary_bytes; }
 	}

@@ -5,7 +5,7 @@
  * eyalroz/libgiddy.  Everything exported by the shared library is declared in
  * this header, `extern "C"`, with plain pointers and sizes only.
  *
- * Two groups of entry points:
+ * Groups of entry points ((1) and (2) mirror the reference; (3) fused decoders and (4) host-resident scans are extensions):
  *
  *  (1) The *registry* API ("mode iii" of the reference, README.md:116-126):
  *      string-keyed factory -> type-erased kernel wrapper -> resolve a launch
@@ -23,13 +23,17 @@
  *      The C++ wrapper classes (include/giddy/) call only these.  Each launcher
  *      cites the reference __global__ function it replaces.
  *
+ *  (3) Fused composite decoders, (4) host-resident scans: see the section comments below.
+ *
  * Conventions: every function returns a giddy_status_t (0 = success) unless it
  * returns a pointer/count; on failure giddy_last_error() holds a message for the
  * calling thread.  Launches are asynchronous on the given stream and -- like the
  * reference (external/cuda-api-wrappers/src/cuda/api/kernel_launch.cuh:107-112) --
  * execution errors surface at the caller's next synchronisation; launch
- * *configuration* errors are reported immediately.  The library owns no device
- * memory, makes no copies and never synchronises.  There is no CPU fallback.
+ * *configuration* errors are reported immediately.  The library owns no column
+ * data and never synchronises; the only device memory it ever takes is the Delta look-back workspace (a few
+ * KB per launch, stream-ordered, from a pool of its own) and the only copies it makes are those a caller records
+ * in a scan (group 4).  There is no CPU fallback.
  */
 #ifndef GIDDY_B200_H_
 #define GIDDY_B200_H_
@@ -330,7 +334,7 @@ GIDDY_API giddy_status_t giddy_b200_compressed_indices_scatter_launch(
 	uint64_t anchoring_period, uint64_t num_scatter_position_runs, uint64_t data_length);
 
 /* ------------------------------------------------------------------------- */
-/* Extensions: fused composite decoders (no counterpart kernel in the          */
+/* (3) Extensions: fused composite decoders (no counterpart kernel in the      */
 /* reference, which composes schemes by running one kernel after another,      */
 /* README.md:55-60).                                                           */
 /* ------------------------------------------------------------------------- */
@@ -386,6 +390,54 @@ GIDDY_API giddy_status_t giddy_b200_patched_frame_of_reference_launch(
 	const void* scatter_position_offset_bytes,
 	const void* scatter_position_anchors,
 	uint64_t anchoring_period, uint64_t num_scatter_position_runs, uint64_t data_length);
+
+/* ------------------------------------------------------------------------- */
+/* (4) Host-resident scans: compressed columns in pinned host memory, copied   */
+/* to the device chunk by chunk on side streams and decoded as they land.      */
+/* No counterpart in the reference, which leaves this to the calling DBMS      */
+/* (README.md:18-24: ship the data over the bus compressed, decompress on the  */
+/* GPU); it is the caller-side half of the drop-in path (BASELINE.json         */
+/* configs[4]).  A scan owns streams, events and the recorded operations --    */
+/* never column data.                                                          */
+/* ------------------------------------------------------------------------- */
+
+typedef struct giddy_scan giddy_scan_t;
+
+/* A plan with `num_streams` side streams on the current device.  Operations are appended chunk by chunk (chunks are
+ * created on first mention) and replayed in the order appended; chunk c runs on side stream c % num_streams. */
+GIDDY_API giddy_status_t giddy_scan_create(unsigned num_streams, giddy_scan_t** out);
+GIDDY_API void           giddy_scan_destroy(giddy_scan_t* scan);
+GIDDY_API unsigned       giddy_scan_num_streams(const giddy_scan_t* scan);
+GIDDY_API unsigned       giddy_scan_num_chunks(const giddy_scan_t* scan);
+GIDDY_API size_t         giddy_scan_num_operations(const giddy_scan_t* scan);
+
+/* cudaMemcpyAsync(device_destination, host_source, bytes, HostToDevice) on the chunk's stream; host_source should be
+ * pinned (cudaHostAlloc / cudaHostRegister) or the copy will not overlap anything. */
+GIDDY_API giddy_status_t giddy_scan_add_copy(giddy_scan_t* scan, unsigned chunk,
+	void* device_destination, const void* host_source, size_t bytes);
+
+/* giddy_kernel_enqueue_launch(kernel, <the chunk's stream>, launch_config, arguments) at this point of the chunk.
+ * The argument array is copied; the kernel object must outlive the scan. */
+GIDDY_API giddy_status_t giddy_scan_add_launch(giddy_scan_t* scan, unsigned chunk, const giddy_kernel_t* kernel,
+	const giddy_launch_config_t* launch_config, const giddy_arg_t* arguments, size_t num_arguments);
+
+/* Anything else a chunk needs enqueued (a caller's own kernel, a device-to-device copy): enqueue(stream, user_data) is
+ * called at every replay and must only enqueue asynchronous work on `stream`. */
+typedef giddy_status_t (*giddy_scan_callback_t)(void* stream, void* user_data);
+GIDDY_API giddy_status_t giddy_scan_add_callback(giddy_scan_t* scan, unsigned chunk,
+	giddy_scan_callback_t enqueue, void* user_data, void (*destroy_user_data)(void*));
+
+/* What is appended to `chunk` from now on waits for what has been appended to `on_chunk` (< chunk) so far -- e.g. the
+ * patches of a chunk whose first targets lie in the previous chunk's output. */
+GIDDY_API giddy_status_t giddy_scan_add_dependency(giddy_scan_t* scan, unsigned chunk, unsigned on_chunk);
+
+/* Replay as one CUDA graph, captured at the next giddy_scan_run() and re-captured after the plan changes, instead of
+ * re-enqueueing every operation (off by default). */
+GIDDY_API giddy_status_t giddy_scan_set_graph_replay(giddy_scan_t* scan, int enabled);
+
+/* Enqueue one scan: the side streams fork from `stream`, run their chunks, and are joined back into `stream`.
+ * Asynchronous; the current device must be the one the scan was created on. */
+GIDDY_API giddy_status_t giddy_scan_run(giddy_scan_t* scan, void* stream);
 
 #ifdef __cplusplus
 } /* extern "C" */

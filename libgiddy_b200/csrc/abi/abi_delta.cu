@@ -1,5 +1,6 @@
 // C ABI launcher for the Delta decoder (include/giddy_b200.h, kernel API).
 // Instantiations: src/kernel_wrappers/decompression/delta.cu:94-106.
+#include <mutex>
 #include "abi_internal.hpp"
 #include "../kernels/delta.cuh"
 
@@ -19,13 +20,70 @@ giddy_status_t delta_launch(void* stream, const giddy_launch_config_t* cfg, void
 		static_cast<uint_t<U>*>(out), static_cast<const uint_t<C>*>(in), static_cast<const uint_t<U>*>(anchors),
 		(size_type<I>) n, (size_type<I>) L);
 }
+// The look-back workspace comes from a pool of this library's own, one per device, which keeps what it has been given
+// (release threshold: never): the default pool hands its memory back to the driver at every synchronisation, and the
+// next launch then pays for mapping it again.
+cudaError_t workspace_pool(cudaMemPool_t* pool)
+{
+	static std::mutex guard;
+	static cudaMemPool_t pools[64] = { };
+	int device = 0;
+	cudaError_t error = cudaGetDevice(&device);
+	if (error != cudaSuccess) { return error; }
+	if (device < 0 || device >= 64) { return cudaDeviceGetDefaultMemPool(pool, device); }
+	std::lock_guard<std::mutex> lock(guard);
+	if (pools[device] == nullptr) {
+		cudaMemPoolProps properties = { };
+		properties.allocType = cudaMemAllocationTypePinned;
+		properties.handleTypes = cudaMemHandleTypeNone;
+		properties.location.type = cudaMemLocationTypeDevice;
+		properties.location.id = device;
+		error = cudaMemPoolCreate(&pools[device], &properties);
+		if (error != cudaSuccess) { pools[device] = nullptr; return error; }
+		unsigned long long keep = ~0ull;
+		cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+	}
+	*pool = pools[device];
+	return cudaSuccess;
+}
+
+// Whether grids can be launched cooperatively on the current device (all CTAs resident at once).
+bool cooperative_launch_supported()
+{
+	int device = 0, supported = 0;
+	if (cudaGetDevice(&device) != cudaSuccess) { return false; }
+	if (cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, device) != cudaSuccess) { return false; }
+	return supported != 0;
+}
+
 template <unsigned I, unsigned U, unsigned C>
 giddy_status_t delta_long_launch(void* stream, const giddy_launch_config_t* cfg, void* out, const void* in, const void* anchors, uint64_t n, uint64_t L,
 	void* workspace)
 {
-	return launch(kernels::delta_decompress_long_segments<I, U, C>, stream, cfg,
-		static_cast<uint_t<U>*>(out), static_cast<const uint_t<C>*>(in), static_cast<const uint_t<U>*>(anchors),
-		(size_type<I>) n, (size_type<I>) L, workspace);
+	auto out_ = static_cast<uint_t<U>*>(out);
+	auto in_ = static_cast<const uint_t<C>*>(in);
+	auto anchors_ = static_cast<const uint_t<U>*>(anchors);
+	size_type<I> n_ = (size_type<I>) n, L_ = (size_type<I>) L;
+	if (cooperative_launch_supported()) {
+		// statically assigned tiles: every CTA must be resident, which a cooperative launch of at most
+		// (CTAs per multiprocessor) x (multiprocessors) CTAs guarantees
+		auto kernel = kernels::delta_decompress_long_segments<I, U, C, true>;
+		int device = 0, multiprocessors = 0, per_multiprocessor = 0;
+		cudaError_t error = cudaGetDevice(&device);
+		if (error == cudaSuccess) { error = cudaDeviceGetAttribute(&multiprocessors, cudaDevAttrMultiProcessorCount, device); }
+		if (error == cudaSuccess) { error = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_multiprocessor, kernel, (int) cfg->block_dimensions[0], 0); }
+		if (error != cudaSuccess) { return fail_cuda(error, "occupancy query (Delta look-back)"); }
+		const unsigned resident = (unsigned) multiprocessors * (unsigned) per_multiprocessor;
+		if (resident > 0) {
+			const unsigned grid = cfg->grid_dimensions[0] < resident ? cfg->grid_dimensions[0] : resident;
+			void* arguments[] = { &out_, &in_, &anchors_, &n_, &L_, &workspace };
+			error = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(cfg->block_dimensions[0]), arguments, 0,
+				static_cast<cudaStream_t>(stream));
+			if (error != cudaSuccess) { return fail_cuda(error, "cooperative kernel launch (Delta look-back)"); }
+			return GIDDY_SUCCESS;
+		}
+	}
+	return launch(kernels::delta_decompress_long_segments<I, U, C, false>, stream, cfg, out_, in_, anchors_, n_, L_, workspace);
 }
 #define DELTA_ENTRY(I, U, C) { I, U, C, reinterpret_cast<const void*>(&kernels::delta_decompress<I, U, C>), &delta_launch<I, U, C>, &delta_long_launch<I, U, C> }
 #define DELTA_ENTRIES(I) DELTA_ENTRY(I, 2, 1), DELTA_ENTRY(I, 4, 1), DELTA_ENTRY(I, 4, 2), DELTA_ENTRY(I, 8, 1), DELTA_ENTRY(I, 8, 2), DELTA_ENTRY(I, 8, 4)
@@ -61,22 +119,28 @@ extern "C" giddy_status_t giddy_b200_delta_launch(
 	// Few, long segments: tiles with decoupled look-back (kernels/delta.cuh).  The tile descriptors live in a
 	// workspace taken from the stream-ordered allocator for the duration of this launch -- allocation, zeroing,
 	// kernel and release are all enqueued on the caller's stream; nothing synchronises and nothing is kept.
-	const unsigned threads = config->block_dimensions[0];
-	if (threads % 32 != 0 || threads == 0) { return fail(GIDDY_INVALID_ARGUMENT, "blocks must be made of whole warps"); }
+	if (config->block_dimensions[0] % 32 != 0 || config->block_dimensions[0] == 0) { return fail(GIDDY_INVALID_ARGUMENT, "blocks must be made of whole warps"); }
+	// the look-back kernel is compiled for CTAs of at most GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS threads; its CTAs are
+	// persistent and draw tiles from a ticket counter, so a larger requested block is simply cut down
+	giddy_launch_config_t long_config = *config;
+	if (long_config.block_dimensions[0] > GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS) { long_config.block_dimensions[0] = GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS; }
+	const unsigned threads = long_config.block_dimensions[0];
 	const unsigned E = 16 / U;
 	const bool vectorizable = reinterpret_cast<uintptr_t>(decompressed) % 16 == 0 &&
 		reinterpret_cast<uintptr_t>(compressed_input) % (E * C) == 0 && segment_length % E == 0;
-	const uint64_t tile_elements = (uint64_t) threads * GIDDY_DELTA_ROWS_PER_STEP * (vectorizable ? E : 1);
+	const uint64_t tile_elements = (uint64_t) threads * GIDDY_DELTA_LOOK_BACK_ROWS * (vectorizable ? E : 1);
 	const uint64_t num_segments = (length + segment_length - 1) / segment_length;
 	const uint64_t num_tiles = num_segments * ((segment_length + tile_elements - 1) / tile_elements); // an upper bound
-	const size_t workspace_bytes = 32 + (size_t) num_tiles * 32;
+	const size_t workspace_bytes = 32 + (size_t) num_tiles * 16;
 	void* workspace = nullptr;
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
-	cudaError_t error = cudaMallocAsync(&workspace, workspace_bytes, s);
-	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocAsync (Delta look-back workspace)"); }
+	cudaMemPool_t pool = nullptr;
+	cudaError_t error = workspace_pool(&pool);
+	if (error == cudaSuccess) { error = cudaMallocFromPoolAsync(&workspace, workspace_bytes, pool, s); }
+	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocFromPoolAsync (Delta look-back workspace)"); }
 	error = cudaMemsetAsync(workspace, 0, workspace_bytes, s);
 	if (error != cudaSuccess) { cudaFreeAsync(workspace, s); return fail_cuda(error, "cudaMemsetAsync (Delta look-back workspace)"); }
-	status = e->launch_long(stream, config, decompressed, compressed_input, anchor_values, length, segment_length, workspace);
+	status = e->launch_long(stream, &long_config, decompressed, compressed_input, anchor_values, length, segment_length, workspace);
 	error = cudaFreeAsync(workspace, s);
 	if (status == GIDDY_SUCCESS && error != cudaSuccess) { return fail_cuda(error, "cudaFreeAsync (Delta look-back workspace)"); }
 	return status;

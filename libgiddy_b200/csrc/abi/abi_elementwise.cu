@@ -188,10 +188,8 @@ extern "C" giddy_status_t giddy_b200_dictionary_launch(
 	giddy_status_t status;
 	if (!check_launch(config, e ? e->kernel : nullptr, status)) { return status; }
 	if (length == 0) { return GIDDY_SUCCESS; }
-	if (cache_dictionary_in_shared_memory && (uint64_t) config->dynamic_shared_memory_size < num_dictionary_entries * U) {
-		return fail(GIDDY_INVALID_ARGUMENT, "caching the dictionary in shared memory needs num_dictionary_entries * sizeof(element) "
-			"bytes of dynamic shared memory in the launch configuration");
-	}
+	// (with caching asked for, the kernel keeps as many leading entries in shared memory as the configuration's dynamic
+	// shared memory holds -- all of them, if it was resolved for this dictionary -- and reads the rest through L1/L2)
 	return e->launch(stream, config, decompressed, compressed_input, dictionary_entries, length, num_dictionary_entries,
 		cache_dictionary_in_shared_memory != 0, (unsigned short) serialization_factor);
 }

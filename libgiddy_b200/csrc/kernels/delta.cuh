@@ -108,75 +108,153 @@ __global__ void delta_decompress(
 // Delta with LONG segments (few anchors, down to a single one: a plain prefix sum over the column).
 // A warp per segment cannot fill the GPU then, so segments are cut into CTA-sized tiles which are scanned
 // in a single pass with decoupled look-back: every tile publishes its aggregate as soon as it has it, and
-// obtains its exclusive prefix by summing its predecessors' aggregates -- 32 descriptors per warp step --
-// back to the nearest tile whose inclusive prefix is already known.  The first tile of every segment knows
-// its prefix at once (the segment's anchor), so a look-back never leaves its segment.
+// obtains its exclusive prefix by summing its predecessors' aggregates back to the nearest tile whose
+// inclusive prefix is already known.  The first tile of every segment knows its prefix at once (the
+// segment's anchor), so a look-back never leaves its segment.
 //
-// Tiles are handed out through a ticket counter, in order, to persistent CTAs, so every tile's
-// predecessors are running or done: the spin-waits cannot deadlock under any grid size.
+// What keeps the look-back off the critical path:
+//   * a descriptor is self-validating -- each 64-bit word carries the status in its upper half and 32 bits
+//     of the value in its lower half -- so publishing is one relaxed store and polling one relaxed load:
+//     no fences, and status and value arrive in the same round trip (a 64-bit value takes two such words
+//     in one 16-byte access; a torn pair shows two different statuses and is polled again);
+//   * a warp inspects look_back_window x 32 predecessors per round trip, so that the distance to the
+//     inclusive-prefix wavefront (tiles started per L2 round trip, ~100 at HBM speed) is covered in one round;
+//   * tiles are large (look_back_rows 16-byte vectors per thread), and the next tile's deltas are already on
+//     their way from HBM while this tile looks back.
 //
-// workspace: 32 zeroed bytes (the ticket counter) followed by one zeroed 32-byte descriptor per tile;
+// Persistent CTAs; a tile's predecessors are always running or done, so the spin-waits cannot deadlock: either
+// the grid is launched cooperatively (all CTAs resident) and CTA b takes tiles b, b + grid, ..., or tiles are
+// handed out in order through a ticket counter (any grid size).
+//
+// workspace: 32 zeroed bytes (the ticket counter) followed by one zeroed 16-byte descriptor per tile;
 // the launcher takes it from the stream-ordered allocator (cudaMallocAsync) for the duration of the launch.
 // -------------------------------------------------------------------------------------------------
 namespace delta_detail {
 
-struct alignas(32) tile_descriptor_t {
-	unsigned long long aggregate;  // sum of the tile's deltas             (valid when status >= 1)
-	unsigned long long inclusive;  // value of the tile's last element     (valid when status == 2)
-	uint32_t           status;
-	uint32_t           padding[3];
-};
+#ifdef GIDDY_DELTA_TRACE  // development aid (benchmarks/micro/lookback_probe.cu): per-tile phase timestamps
+__device__ unsigned long long trace[1 << 20];
+__device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define GIDDY_DELTA_TRACE_POINT(tile, k) do { if (threadIdx.x == 0 && (tile) < (1u << 17)) { trace[(tile) * 8 + (k)] = trace_now(); } } while (0)
+#define GIDDY_DELTA_TRACE_VALUE(tile, k, v) do { if (threadIdx.x == 0 && (tile) < (1u << 17)) { trace[(tile) * 8 + (k)] = (v); } } while (0)
+#else
+#define GIDDY_DELTA_TRACE_POINT(tile, k) do { } while (0)
+#define GIDDY_DELTA_TRACE_VALUE(tile, k, v) do { } while (0)
+#endif
+
+constexpr unsigned look_back_rows   = GIDDY_DELTA_LOOK_BACK_ROWS;
+constexpr unsigned look_back_window = GIDDY_DELTA_LOOK_BACK_WINDOW; // descriptors per lane per round
+
+struct alignas(16) tile_descriptor_t { unsigned long long word[2]; };
 enum : uint32_t { tile_unknown = 0, tile_has_aggregate = 1, tile_has_inclusive = 2 };
 
-__device__ __forceinline__ void store_release(uint32_t* p, uint32_t v)
-{
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t load_acquire(const uint32_t* p)
-{
-	uint32_t v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ unsigned long long load_relaxed(const unsigned long long* p)
-{
-	unsigned long long v;
-	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void store_relaxed(unsigned long long* p, unsigned long long v)
-{
-	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-
-// The exclusive prefix of tile `tile`, the `tile_in_segment`-th (>= 1) of its segment; called by one whole warp.
 template <unsigned U>
-__device__ __forceinline__ uint_t<U> look_back(tile_descriptor_t* descriptors, uint64_t tile, uint64_t tile_in_segment)
+__device__ __forceinline__ void publish(tile_descriptor_t* d, uint32_t status, uint_t<U> value)
 {
-	const unsigned lane = lane_index();
-	uint_t<U> exclusive = 0;
-	uint64_t looked = 0; // predecessors already summed
-	while (true) {
-		const bool valid = looked + lane < tile_in_segment;
-		uint32_t status = tile_unknown;
-		tile_descriptor_t* d = descriptors + (tile - 1 - looked - lane);
-		if (valid) { do { status = load_acquire(&d->status); } while (status == tile_unknown); }
-		const unsigned with_inclusive = __ballot_sync(full_mask, valid && status == tile_has_inclusive);
-		const unsigned nearest = with_inclusive ? (unsigned) __ffs((int) with_inclusive) - 1 : warp_size; // lanes beyond it do not count
-		uint_t<U> mine = 0;
-		if (valid && lane <= nearest) { mine = (uint_t<U>) load_relaxed(lane == nearest ? &d->inclusive : &d->aggregate); }
-		#pragma unroll
-		for (unsigned delta = warp_size / 2; delta > 0; delta >>= 1) {
-			if (sizeof(uint_t<U>) <= 4) { mine = (uint_t<U>)(mine + (uint_t<U>) __shfl_xor_sync(full_mask, (uint32_t) mine, delta)); }
-			else { mine = (uint_t<U>)(mine + (uint_t<U>) __shfl_xor_sync(full_mask, (unsigned long long) mine, delta)); }
-		}
-		exclusive = (uint_t<U>)(exclusive + mine);
-		if (with_inclusive) { return exclusive; }
-		looked += warp_size;
+	const unsigned long long tag = (unsigned long long) status << 32;
+	if (U <= 4) {
+		asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(d), "l"(tag | (unsigned long long)(uint32_t) value) : "memory");
+	}
+	else {
+		const unsigned long long v = (unsigned long long) value;
+		asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(d), "l"(tag | (v & 0xffffffffull)), "l"(tag | (v >> 32)) : "memory");
 	}
 }
 
-template <unsigned U, unsigned C, unsigned E>
+// the descriptor's status, and its value if the status is not tile_unknown
+template <unsigned U>
+__device__ __forceinline__ uint32_t peek(const tile_descriptor_t* d, uint_t<U>& value)
+{
+	if (U <= 4) {
+		unsigned long long w;
+		asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(d) : "memory");
+		value = (uint_t<U>) w;
+		return (uint32_t)(w >> 32);
+	}
+	else {
+		unsigned long long w0, w1;
+		asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(d) : "memory");
+		value = (uint_t<U>)((w0 & 0xffffffffull) | (w1 << 32));
+		const uint32_t s0 = (uint32_t)(w0 >> 32), s1 = (uint32_t)(w1 >> 32);
+		return s0 == s1 ? s0 : (uint32_t) tile_unknown;
+	}
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T x)
+{
+	if constexpr (sizeof(T) <= 4) { return (T) __reduce_add_sync(full_mask, (unsigned) x); }
+	else {
+		#pragma unroll
+		for (unsigned delta = warp_size / 2; delta > 0; delta >>= 1) { x = (T)(x + (T) __shfl_xor_sync(full_mask, (unsigned long long) x, delta)); }
+		return x;
+	}
+}
+
+// The exclusive prefix of tile `tile`, the `tile_in_segment`-th (>= 1) of its segment; called by one whole warp.
+// A round inspects the look_back_window x 32 nearest predecessors not yet summed, all lanes polling at once; it
+// ends as soon as the descriptors up to the nearest one with an inclusive prefix have been seen (farther ones are
+// never waited for), or when all of them hold just aggregates.
+template <unsigned U>
+__device__ __forceinline__ uint_t<U> look_back(const tile_descriptor_t* descriptors, uint64_t tile, uint64_t tile_in_segment)
+{
+	unsigned polls = 0, rounds = 0; (void) polls; (void) rounds;
+	const unsigned lane = lane_index();
+	constexpr unsigned round_tiles = look_back_window * warp_size;
+	uint_t<U> exclusive = 0;
+	uint64_t looked = 0; // predecessors already summed
+	while (true) {
+		uint_t<U> value[look_back_window];
+		uint32_t status[look_back_window];
+		bool valid[look_back_window];
+		#pragma unroll
+		for (unsigned q = 0; q < look_back_window; q++) {
+			valid[q] = looked + q * warp_size + lane < tile_in_segment; // distance 0 = the immediate predecessor
+			status[q] = tile_unknown; value[q] = 0;
+		}
+		unsigned nearest; // distance (within this round) of the nearest tile with an inclusive prefix; round_tiles: none
+		rounds++;
+		while (true) {
+			polls++;
+			#pragma unroll
+			for (unsigned q = 0; q < look_back_window; q++) {
+				if (valid[q] && status[q] == tile_unknown) {
+					status[q] = peek<U>(descriptors + (tile - 1 - (looked + q * warp_size + lane)), value[q]);
+				}
+			}
+			nearest = round_tiles;
+			bool all_seen = true;
+			#pragma unroll
+			for (unsigned q = 0; q < look_back_window; q++) {
+				const unsigned unseen = __ballot_sync(full_mask, valid[q] && status[q] == tile_unknown);
+				const unsigned with_inclusive = __ballot_sync(full_mask, valid[q] && status[q] == tile_has_inclusive);
+				if (all_seen && nearest == round_tiles) {
+					const unsigned seen_prefix = unseen ? ((1u << (__ffs((int) unseen) - 1)) - 1u) : full_mask; // lanes before the first unseen one
+					const unsigned usable = with_inclusive & seen_prefix;
+					if (usable) { nearest = q * warp_size + (unsigned) __ffs((int) usable) - 1; }
+					else if (unseen) { all_seen = false; }
+				}
+			}
+			if (nearest != round_tiles || all_seen) { break; }
+		}
+		uint_t<U> mine = 0;
+		#pragma unroll
+		for (unsigned q = 0; q < look_back_window; q++) {
+			if (valid[q] && q * warp_size + lane <= nearest) { mine = (uint_t<U>)(mine + value[q]); }
+		}
+		exclusive = (uint_t<U>)(exclusive + warp_sum(mine));
+		if (nearest != round_tiles) { GIDDY_DELTA_TRACE_VALUE(tile, 6, polls); GIDDY_DELTA_TRACE_VALUE(tile, 7, rounds); return exclusive; }
+		looked += round_tiles;
+	}
+}
+
+// Static == true : CTA b decodes tiles b, b + gridDim.x, ... -- needs every CTA of the grid resident at once (a
+//                   cooperative launch guarantees it), so that no tile waits for one whose CTA has not started.  The
+//                   order being known, the next tile's deltas are requested before this tile's look-back begins.
+// Static == false: tiles are drawn from a ticket counter, in order, so that every tile's predecessors are running or
+//                   done whatever the grid -- the fall-back where a cooperative launch is not to be had.  (Drawing
+//                   tickets ahead of time is not an option: a drawn but unstarted tile stalls all its successors,
+//                   and the stalls chain up -- measured 20x slower.)
+template <unsigned U, unsigned C, unsigned E, bool Static>
 __device__ __forceinline__ void decode_tiles_with_look_back(
 	uint_t<U>*        __restrict__  decompressed,
 	const uint_t<C>*  __restrict__  compressed_input,
@@ -185,111 +263,202 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 	uint64_t                        segment_length,
 	void*                           workspace)
 {
-	__shared__ uint_t<U> warp_totals[32];
-	__shared__ uint_t<U> shared_tile_exclusive;
-	__shared__ uint64_t  shared_ticket;
+	// double-buffered by tile parity, so that two barriers per tile are enough
+	__shared__ uint_t<U> warp_totals[2][32];
+	__shared__ uint_t<U> shared_tile_exclusive[2];
+	__shared__ uint64_t  shared_ticket[2];
 
 	const unsigned lane = lane_index(), warp = warp_index_in_block(), num_warps = warps_per_block();
 	constexpr unsigned row_elements = warp_size * E;
-	const uint64_t tile_elements = (uint64_t) num_warps * rows_per_step * row_elements;
+	const uint64_t tile_elements = (uint64_t) num_warps * look_back_rows * row_elements;
 	const uint64_t tiles_per_segment = (segment_length + tile_elements - 1) / tile_elements;
 	const uint64_t num_segments = (length + segment_length - 1) / segment_length;
 	const uint64_t last_segment_length = length - (num_segments - 1) * segment_length;
 	const uint64_t num_tiles = (num_segments - 1) * tiles_per_segment + (last_segment_length + tile_elements - 1) / tile_elements;
 	unsigned long long* const ticket_counter = static_cast<unsigned long long*>(workspace);
 	tile_descriptor_t* const descriptors = reinterpret_cast<tile_descriptor_t*>(static_cast<unsigned char*>(workspace) + 32);
+	const uint64_t warp_offset = (uint64_t) warp * look_back_rows * row_elements + lane * E;
 
-	while (true) {
-		if (threadIdx.x == 0) { shared_ticket = atomicAdd(ticket_counter, 1ull); }
-		__syncthreads();
-		const uint64_t tile = shared_ticket;
-		if (tile >= num_tiles) { return; }
-		const uint64_t segment = tile / tiles_per_segment, tile_in_segment = tile - segment * tiles_per_segment;
-		const uint64_t segment_start = segment * segment_length;
-		const uint64_t this_segment_length = minimum(segment_length, length - segment_start);
-		const uint64_t tile_offset = tile_in_segment * tile_elements;
-		const uint64_t tile_start = segment_start + tile_offset;
-		const uint64_t tile_length = minimum(tile_elements, this_segment_length - tile_offset);
-		const uint64_t warp_offset = (uint64_t) warp * rows_per_step * row_elements;
-
-		byte_pack<E * C> deltas[rows_per_step];
+	struct geometry_t { uint64_t segment, tile_in_segment, start, length; };
+	auto locate = [&](uint64_t tile) {
+		geometry_t g;
+		g.segment = tile / tiles_per_segment;
+		g.tile_in_segment = tile - g.segment * tiles_per_segment;
+		const uint64_t segment_start = g.segment * segment_length;
+		const uint64_t offset = g.tile_in_segment * tile_elements;
+		g.start = segment_start + offset;
+		g.length = minimum(tile_elements, minimum(segment_length, length - segment_start) - offset);
+		return g;
+	};
+	auto request = [&](byte_pack<E * C> (&deltas)[look_back_rows], const geometry_t& g) {
 		#pragma unroll
-		for (unsigned r = 0; r < rows_per_step; r++) {
-			const uint64_t p = warp_offset + r * row_elements + lane * E;
-			if (p + E <= tile_length) { deltas[r] = load_pack<E * C>(compressed_input + tile_start + p); }
+		for (unsigned r = 0; r < look_back_rows; r++) {
+			const uint64_t p = warp_offset + r * row_elements;
+			if (p + E <= g.length) { deltas[r] = load_pack<E * C>(compressed_input + g.start + p); }
 			else {
 				#pragma unroll
-				for (unsigned j = 0; j < E; j++) { deltas[r].template set<C>(j, (p + j < tile_length) ? compressed_input[tile_start + p + j] : (uint_t<C>) 0); }
+				for (unsigned j = 0; j < E; j++) { deltas[r].template set<C>(j, (p + j < g.length) ? compressed_input[g.start + p + j] : (uint_t<C>) 0); }
 			}
 		}
-		// within the warp: what precedes each lane's elements of each row
-		uint_t<U> before[rows_per_step];
-		uint_t<U> warp_total = 0;
+	};
+	// the warp's total first (one reduction): the tile's aggregate is published as early as possible and nothing but
+	// the deltas stays in registers across the look-back; the scans proper come afterwards
+	auto publish_warp_total = [&](const byte_pack<E * C> (&deltas)[look_back_rows], unsigned parity) {
+		uint_t<U> lane_total = 0;
 		#pragma unroll
-		for (unsigned r = 0; r < rows_per_step; r++) {
-			uint_t<U> sum = 0;
+		for (unsigned r = 0; r < look_back_rows; r++) {
 			#pragma unroll
-			for (unsigned j = 0; j < E; j++) { sum = (uint_t<U>)(sum + (uint_t<U>) deltas[r].template get<C>(j)); }
-			const uint_t<U> inclusive = warp_inclusive_sum(sum);
-			before[r] = (uint_t<U>)(warp_total + (uint_t<U>)(inclusive - sum));
-			warp_total = (uint_t<U>)(warp_total + shuffle_from(inclusive, warp_size - 1));
+			for (unsigned j = 0; j < E; j++) { lane_total = (uint_t<U>)(lane_total + (uint_t<U>) deltas[r].template get<C>(j)); }
 		}
-		if (lane == 0) { warp_totals[warp] = warp_total; }
-		__syncthreads();
+		const uint_t<U> warp_total = warp_sum(lane_total);
+		if (lane == 0) { warp_totals[parity][warp] = warp_total; }
+	};
+	// after the barrier: warp 0 settles the tile's exclusive prefix; returns what precedes this warp inside the tile
+	auto settle_prefix = [&](uint64_t tile, const geometry_t& g, unsigned parity) {
 		uint_t<U> preceding_warps = 0, tile_aggregate = 0;
 		for (unsigned w = 0; w < num_warps; w++) {
-			const uint_t<U> t = warp_totals[w];
+			const uint_t<U> t = warp_totals[parity][w];
 			if (w < warp) { preceding_warps = (uint_t<U>)(preceding_warps + t); }
 			tile_aggregate = (uint_t<U>)(tile_aggregate + t);
 		}
 		if (warp == 0) {
 			tile_descriptor_t* mine = descriptors + tile;
 			uint_t<U> exclusive;
-			if (tile_in_segment == 0) { exclusive = __ldg(anchor_values + segment); }
+			if (g.tile_in_segment == 0) { exclusive = __ldg(anchor_values + g.segment); }
 			else {
-				if (lane == 0) {
-					store_relaxed(&mine->aggregate, (unsigned long long) tile_aggregate);
-					store_release(&mine->status, tile_has_aggregate);
-				}
-				exclusive = look_back<U>(descriptors, tile, tile_in_segment);
+				if (lane == 0) { publish<U>(mine, tile_has_aggregate, tile_aggregate); }
+				exclusive = look_back<U>(descriptors, tile, g.tile_in_segment);
 			}
 			if (lane == 0) {
-				store_relaxed(&mine->inclusive, (unsigned long long)(uint_t<U>)(exclusive + tile_aggregate));
-				store_release(&mine->status, tile_has_inclusive);
-				shared_tile_exclusive = exclusive;
+				publish<U>(mine, tile_has_inclusive, (uint_t<U>)(exclusive + tile_aggregate));
+				shared_tile_exclusive[parity] = exclusive;
+				if (!Static) { shared_ticket[parity ^ 1u] = atomicAdd(ticket_counter, 1ull); }
 			}
 		}
-		__syncthreads();
-		const uint_t<U> base = (uint_t<U>)(shared_tile_exclusive + preceding_warps);
+		return preceding_warps;
+	};
+	auto scan_and_store = [&](const byte_pack<E * C> (&deltas)[look_back_rows], const geometry_t& g, uint_t<U> carry) {
 		#pragma unroll
-		for (unsigned r = 0; r < rows_per_step; r++) {
-			const uint64_t p = warp_offset + r * row_elements + lane * E;
-			uint_t<U> running = (uint_t<U>)(base + before[r]);
-			if (E > 1 && p + E <= tile_length) {
+		for (unsigned r = 0; r < look_back_rows; r++) {
+			const uint64_t p = warp_offset + r * row_elements;
+			uint_t<U> local[E];
+			uint_t<U> sum = 0;
+			#pragma unroll
+			for (unsigned j = 0; j < E; j++) {
+				sum = (uint_t<U>)(sum + (uint_t<U>) deltas[r].template get<C>(j));
+				local[j] = sum;
+			}
+			const uint_t<U> inclusive = warp_inclusive_sum(sum);
+			const uint_t<U> before = (uint_t<U>)(carry + (uint_t<U>)(inclusive - sum));
+			carry = (uint_t<U>)(carry + shuffle_from(inclusive, warp_size - 1));
+			if (E > 1 && p + E <= g.length) {
 				byte_pack<16> vec;
 				#pragma unroll
-				for (unsigned j = 0; j < E; j++) {
-					running = (uint_t<U>)(running + (uint_t<U>) deltas[r].template get<C>(j));
-					vec.template set<U>(j, running);
-				}
-				store_pack_16(decompressed + tile_start + p, vec);
+				for (unsigned j = 0; j < E; j++) { vec.template set<U>(j, (uint_t<U>)(before + local[j])); }
+				store_pack_16(decompressed + g.start + p, vec);
 			}
 			else {
 				#pragma unroll
-				for (unsigned j = 0; j < E; j++) {
-					running = (uint_t<U>)(running + (uint_t<U>) deltas[r].template get<C>(j));
-					if (p + j < tile_length) { decompressed[tile_start + p + j] = running; }
-				}
+				for (unsigned j = 0; j < E; j++) { if (p + j < g.length) { decompressed[g.start + p + j] = (uint_t<U>)(before + local[j]); } }
 			}
 		}
-		__syncthreads(); // shared_ticket and warp_totals are rewritten by the next tile
+	};
+
+	if (Static) {
+		// Software pipeline, one barrier per tile.  While warp 0 looks back for tile k, the other warps wait for tile
+		// k+1's deltas (requested at the top of the iteration) and reduce them; after the barrier tile k+1's aggregate
+		// is published -- a whole scan-and-store phase before its own look-back begins, so that by then the
+		// neighbouring CTAs' aggregates are normally there and look-backs rarely have to poll twice -- and only
+		// then tile k is scanned and stored.
+		__shared__ uint_t<U> totals[3][32];   // [tile ordinal % 3]: written an iteration ahead, read in two iterations
+		__shared__ uint_t<U> exclusives[2];
+		auto publish_totals = [&](const byte_pack<E * C> (&deltas)[look_back_rows], unsigned slot) {
+			uint_t<U> lane_total = 0;
+			#pragma unroll
+			for (unsigned r = 0; r < look_back_rows; r++) {
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) { lane_total = (uint_t<U>)(lane_total + (uint_t<U>) deltas[r].template get<C>(j)); }
+			}
+			const uint_t<U> warp_total = warp_sum(lane_total);
+			if (lane == 0) { totals[slot][warp] = warp_total; }
+		};
+		// thread 0, after the barrier: the tile's aggregate -- or, for a segment's first tile, already its inclusive prefix
+		auto publish_early = [&](uint64_t tile, const geometry_t& g, unsigned slot) {
+			uint_t<U> aggregate = 0;
+			for (unsigned w = 0; w < num_warps; w++) { aggregate = (uint_t<U>)(aggregate + totals[slot][w]); }
+			if (g.tile_in_segment == 0) { publish<U>(descriptors + tile, tile_has_inclusive, (uint_t<U>)(__ldg(anchor_values + g.segment) + aggregate)); }
+			else { publish<U>(descriptors + tile, tile_has_aggregate, aggregate); }
+		};
+
+		uint64_t tile = blockIdx.x;
+		if (tile >= num_tiles) { return; }
+		geometry_t g = locate(tile);
+		byte_pack<E * C> deltas[look_back_rows], next_deltas[look_back_rows];
+		request(deltas, g);
+		publish_totals(deltas, 0);
+		__syncthreads();
+		if (threadIdx.x == 0) { publish_early(tile, g, 0); }
+
+		for (unsigned ordinal = 0; ; ordinal++) {
+			const unsigned slot = ordinal % 3, next_slot = (ordinal + 1) % 3, parity = ordinal & 1u;
+			const uint64_t next_tile = tile + gridDim.x;
+			const bool has_next = next_tile < num_tiles;
+			geometry_t next_g = g;
+			GIDDY_DELTA_TRACE_POINT(tile, 0);
+			if (has_next) { next_g = locate(next_tile); request(next_deltas, next_g); }
+			if (warp == 0) {
+				uint_t<U> exclusive;
+				if (g.tile_in_segment == 0) { exclusive = __ldg(anchor_values + g.segment); }
+				else {
+					exclusive = look_back<U>(descriptors, tile, g.tile_in_segment);
+					if (lane == 0) {
+						uint_t<U> aggregate = 0;
+						for (unsigned w = 0; w < num_warps; w++) { aggregate = (uint_t<U>)(aggregate + totals[slot][w]); }
+						publish<U>(descriptors + tile, tile_has_inclusive, (uint_t<U>)(exclusive + aggregate));
+					}
+				}
+				if (lane == 0) { exclusives[parity] = exclusive; }
+			}
+			GIDDY_DELTA_TRACE_POINT(tile, 1);
+			if (has_next) { publish_totals(next_deltas, next_slot); }
+			GIDDY_DELTA_TRACE_POINT(tile, 2);
+			__syncthreads();
+			GIDDY_DELTA_TRACE_POINT(tile, 3);
+			if (has_next && threadIdx.x == 0) { publish_early(next_tile, next_g, next_slot); }
+			GIDDY_DELTA_TRACE_POINT(tile, 4);
+			uint_t<U> carry = exclusives[parity];
+			for (unsigned w = 0; w < warp; w++) { carry = (uint_t<U>)(carry + totals[slot][w]); }
+			scan_and_store(deltas, g, carry);
+			GIDDY_DELTA_TRACE_POINT(tile, 5);
+			if (!has_next) { return; }
+			#pragma unroll
+			for (unsigned r = 0; r < look_back_rows; r++) { deltas[r] = next_deltas[r]; }
+			tile = next_tile; g = next_g;
+		}
+	}
+	else {
+		if (threadIdx.x == 0) { shared_ticket[0] = atomicAdd(ticket_counter, 1ull); }
+		__syncthreads();
+		for (unsigned parity = 0; ; parity ^= 1u) {
+			const uint64_t tile = shared_ticket[parity];
+			if (tile >= num_tiles) { return; }
+			const geometry_t g = locate(tile);
+			byte_pack<E * C> deltas[look_back_rows];
+			request(deltas, g);
+			publish_warp_total(deltas, parity);
+			__syncthreads();
+			const uint_t<U> preceding_warps = settle_prefix(tile, g, parity);
+			__syncthreads();
+			scan_and_store(deltas, g, (uint_t<U>)(shared_tile_exclusive[parity] + preceding_warps));
+		}
 	}
 }
 
 } // namespace delta_detail
 
-template <unsigned IndexSize, unsigned U, unsigned C>
-__global__ void delta_decompress_long_segments(
+template <unsigned IndexSize, unsigned U, unsigned C, bool Static>
+__global__ void __launch_bounds__(GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS, GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR)
+delta_decompress_long_segments(
 	uint_t<U>*        __restrict__  decompressed,
 	const uint_t<C>*  __restrict__  compressed_input,
 	const uint_t<U>*  __restrict__  anchor_values,
@@ -299,8 +468,8 @@ __global__ void delta_decompress_long_segments(
 {
 	constexpr unsigned E = 16 / U;
 	const bool vectorizable = is_aligned_to(decompressed, 16) && is_aligned_to(compressed_input, E * C) && (segment_length % E == 0);
-	if (vectorizable) { delta_detail::decode_tiles_with_look_back<U, C, E>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
-	else              { delta_detail::decode_tiles_with_look_back<U, C, 1>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
+	if (vectorizable) { delta_detail::decode_tiles_with_look_back<U, C, E, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
+	else              { delta_detail::decode_tiles_with_look_back<U, C, 1, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
 }
 
 } // namespace kernels

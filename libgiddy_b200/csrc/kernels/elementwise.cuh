@@ -276,47 +276,63 @@ __global__ void dictionary_decompress(
 	constexpr unsigned unroll = detail::elementwise_unroll;
 	const uint64_t global_thread = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
 
-	const uint_t<U>* table = dictionary_entries;
+	// As many of the dictionary's leading entries as the launch's dynamic shared memory holds are served from there
+	// (all of them, normally; a dictionary which does not fit keeps its head -- where a frequency-ordered dictionary
+	// has its hot entries -- in shared memory and its tail behind the read-only L1/L2 path).
+	const uint_t<U>* const cached = reinterpret_cast<const uint_t<U>*>(dynamic_shared_memory);
+	uint64_t num_cached = 0;
 	if (cache_dictionary_in_shared_memory) {
-		auto cached = reinterpret_cast<uint_t<U>*>(dynamic_shared_memory);
-		for (uint64_t i = threadIdx.x; i < num_dictionary_entries; i += blockDim.x) { cached[i] = __ldg(dictionary_entries + i); }
+		num_cached = minimum<uint64_t>(num_dictionary_entries, dynamic_shared_memory_size() / U);
+		auto destination = reinterpret_cast<uint_t<U>*>(dynamic_shared_memory);
+		for (uint64_t i = threadIdx.x; i < num_cached; i += blockDim.x) { destination[i] = __ldg(dictionary_entries + i); }
 		__syncthreads();
-		table = cached;
 	}
-	auto lookup = [&](uint_t<DI> index) -> uint_t<U> {
-		return cache_dictionary_in_shared_memory ? table[index] : __ldg(table + index);
+
+	auto decode = [&](auto lookup) {
+		if (!(is_aligned_to(decompressed, 16) && is_aligned_to(compressed_input, in_bytes))) {
+			for (uint64_t p = global_thread; p < length; p += (uint64_t) gridDim.x * blockDim.x) {
+				decompressed[p] = lookup(compressed_input[p]);
+			}
+			return;
+		}
+		const uint64_t num_vectors = length / E;
+		const uint64_t vectors_per_tile = (uint64_t) blockDim.x * unroll;
+		#pragma unroll 1
+		for (uint64_t tile_start = (uint64_t) blockIdx.x * vectors_per_tile; tile_start < num_vectors;
+		     tile_start += (uint64_t) gridDim.x * vectors_per_tile)
+		{
+			byte_pack<in_bytes> in[unroll];
+			#pragma unroll
+			for (unsigned k = 0; k < unroll; k++) {
+				uint64_t v = tile_start + (uint64_t) k * blockDim.x + threadIdx.x;
+				if (v < num_vectors) { in[k] = load_pack<in_bytes>(compressed_input + v * E); }
+			}
+			#pragma unroll
+			for (unsigned k = 0; k < unroll; k++) {
+				uint64_t v = tile_start + (uint64_t) k * blockDim.x + threadIdx.x;
+				if (v >= num_vectors) { continue; }
+				byte_pack<16> out;
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) { out.template set<U>(j, lookup(in[k].template get<DI>(j))); }
+				store_pack_16(decompressed + v * E, out);
+			}
+		}
+		uint64_t tail_position = num_vectors * E + global_thread;
+		if (tail_position < length) { decompressed[tail_position] = lookup(compressed_input[tail_position]); }
 	};
 
-	if (!(is_aligned_to(decompressed, 16) && is_aligned_to(compressed_input, in_bytes))) {
-		for (uint64_t p = global_thread; p < length; p += (uint64_t) gridDim.x * blockDim.x) {
-			decompressed[p] = lookup(compressed_input[p]);
-		}
-		return;
+	// One instance of the loop (three would cost its register allotment and with it two resident CTAs per
+	// multiprocessor).  Fully cached is the common case: the comparison below is then uniformly true.
+	if (num_cached >= num_dictionary_entries && num_cached != 0) { num_cached = ~(uint64_t) 0; }
+	const uint32_t cached_limit = (uint32_t) minimum<uint64_t>(num_cached, 0xffffffffu); // indices below it are served from shared memory
+	if (sizeof(uint_t<DI>) > 4 && num_cached > 0xffffffffull) {
+		decode([&](uint_t<DI> index) -> uint_t<U> { return cached[index]; });
 	}
-	const uint64_t num_vectors = length / E;
-	const uint64_t vectors_per_tile = (uint64_t) blockDim.x * unroll;
-	#pragma unroll 1
-	for (uint64_t tile_start = (uint64_t) blockIdx.x * vectors_per_tile; tile_start < num_vectors;
-	     tile_start += (uint64_t) gridDim.x * vectors_per_tile)
-	{
-		byte_pack<in_bytes> in[unroll];
-		#pragma unroll
-		for (unsigned k = 0; k < unroll; k++) {
-			uint64_t v = tile_start + (uint64_t) k * blockDim.x + threadIdx.x;
-			if (v < num_vectors) { in[k] = load_pack<in_bytes>(compressed_input + v * E); }
-		}
-		#pragma unroll
-		for (unsigned k = 0; k < unroll; k++) {
-			uint64_t v = tile_start + (uint64_t) k * blockDim.x + threadIdx.x;
-			if (v >= num_vectors) { continue; }
-			byte_pack<16> out;
-			#pragma unroll
-			for (unsigned j = 0; j < E; j++) { out.template set<U>(j, lookup(in[k].template get<DI>(j))); }
-			store_pack_16(decompressed + v * E, out);
-		}
+	else {
+		decode([&](uint_t<DI> index) -> uint_t<U> {
+			return ((uint64_t) index < (uint64_t) cached_limit || cached_limit == 0xffffffffu) ? cached[index] : __ldg(dictionary_entries + index);
+		});
 	}
-	uint64_t tail_position = num_vectors * E + global_thread;
-	if (tail_position < length) { decompressed[tail_position] = lookup(compressed_input[tail_position]); }
 }
 
 } // namespace kernels

@@ -71,12 +71,27 @@ __device__ __forceinline__ uint64_t load_offset(const uint8_t* __restrict__ run_
 // bytes; anchoring period a covers the runs [anchors[a], anchors[a+1]) and patch values from a*A.
 //   target[(OI)(baseline[r] + offset_r[j])] = data[k],  k advancing through the runs in order.
 //
-// A warp owns an anchoring period.  The metadata of 32 runs is loaded at once (one run per lane),
-// a warp scan of the run lengths locates each run's first patch value, and the runs are then
-// walked with the lanes striding over each run's patches -- so a period costs one metadata
-// round-trip per 32 runs instead of one per run (the reference reads each run's metadata serially,
-// :83-124).
+// A warp owns an anchoring period.  The metadata of 32 runs is loaded at once (one run per lane) and
+// parked in the warp's slice of shared memory together with a warp scan of the run lengths; the patches
+// of those runs are then treated as one flat list: lane-strided, each patch finds its run with a 5-step
+// branch-free search of the scanned lengths, and ci_unroll patches per lane have their offset and value
+// loads in flight at once.  So a period costs one metadata round trip per 32 runs plus one per 32 x
+// ci_unroll patches, however short its runs are (the reference handles the runs one after the other,
+// with a dependent metadata read and a block-stride loop each, :83-124).
 // -------------------------------------------------------------------------------------------------
+namespace ci_detail {
+
+constexpr unsigned ci_unroll = 4;
+
+struct staged_runs_t {
+	uint64_t ends[warp_size];           // inclusive scan of the staged runs' lengths
+	uint64_t baselines[warp_size];
+	uint64_t offset_starts[warp_size];  // byte offset of the run's first offset
+	uint8_t  widths[warp_size];         // bytes per offset
+};
+
+} // namespace ci_detail
+
 template <unsigned OutputIndexSize, unsigned ElementSize, unsigned InputIndexSize, unsigned RunLengthSize>
 __global__ void compressed_indices_scatter(
 	uint_t<ElementSize>*            __restrict__  target,
@@ -91,6 +106,9 @@ __global__ void compressed_indices_scatter(
 	uint_t<InputIndexSize>                        num_scatter_position_runs,
 	size_type<InputIndexSize>                     data_length)
 {
+	using namespace ci_detail;
+	__shared__ staged_runs_t staged_by_warp[32];
+	staged_runs_t& staged = staged_by_warp[warp_index_in_block()];
 	const unsigned lane = lane_index();
 	const uint64_t period_length = anchoring_period;
 	const uint64_t num_periods = ((uint64_t) data_length + period_length - 1) / period_length;
@@ -101,32 +119,42 @@ __global__ void compressed_indices_scatter(
 		const uint64_t past_last_run = reaches_end ? (uint64_t) num_scatter_position_runs : (uint64_t) __ldg(scatter_position_anchors + period + 1);
 		uint64_t next_value = period * period_length; // index into data of the next run's first patch
 
-		for (uint64_t chunk_first_run = first_run; chunk_first_run < past_last_run; chunk_first_run += warp_size) {
+		for (uint64_t chunk_first_run = first_run; chunk_first_run < past_last_run && next_value < data_length; chunk_first_run += warp_size) {
 			const uint64_t run = chunk_first_run + lane;
 			const bool valid = run < past_last_run;
-			const uint64_t my_length   = valid ? (uint64_t) __ldg(scatter_position_run_lengths + run) : 0;
-			const unsigned my_width    = valid ? (unsigned) __ldg(scatter_position_run_individual_offset_sizes + run) / 8 : 1;
-			const uint64_t my_baseline = valid ? (uint64_t) __ldg(scatter_position_run_baseline_values + run) : 0;
-			const uint64_t my_offsets  = valid ? (uint64_t) __ldg(scatter_position_run_offsets_start_positions + run) * OutputIndexSize : 0;
+			const uint64_t my_length = valid ? (uint64_t) __ldg(scatter_position_run_lengths + run) : 0;
+			__syncwarp(); // every lane is done with the previous chunk
+			staged.widths[lane]        = valid ? (uint8_t)(__ldg(scatter_position_run_individual_offset_sizes + run) / 8) : (uint8_t) 1;
+			staged.baselines[lane]     = valid ? (uint64_t) __ldg(scatter_position_run_baseline_values + run) : 0;
+			staged.offset_starts[lane] = valid ? (uint64_t) __ldg(scatter_position_run_offsets_start_positions + run) * OutputIndexSize : 0;
 			const uint64_t inclusive = warp_inclusive_sum(my_length);
-			const uint64_t my_first_value = next_value + (inclusive - my_length);
-			next_value += shuffle_from(inclusive, warp_size - 1);
-			const unsigned runs_in_chunk = (unsigned) minimum<uint64_t>(warp_size, past_last_run - chunk_first_run);
+			staged.ends[lane] = inclusive; // (lanes without a run repeat the total: the search never lands on them)
+			__syncwarp();
+			const uint64_t chunk_patches = shuffle_from(inclusive, warp_size - 1);
+			const uint64_t limit = minimum<uint64_t>(chunk_patches, data_length - next_value);
 
-			for (unsigned r = 0; r < runs_in_chunk; r++) {
-				const uint64_t length      = shuffle_from(my_length, r);
-				const unsigned width       = shuffle_from(my_width, r);
-				const uint64_t baseline    = shuffle_from(my_baseline, r);
-				const uint64_t first_value = shuffle_from(my_first_value, r);
-				const uint8_t* run_offsets = scatter_position_offset_bytes + shuffle_from(my_offsets, r);
-				for (uint64_t j = lane; j < length; j += warp_size) {
-					const uint64_t k = first_value + j;
-					if (k >= data_length) { break; }
-					const uint_t<OutputIndexSize> position =
-						(uint_t<OutputIndexSize>)(baseline + ci_detail::load_offset(run_offsets, j, width));
-					target[position] = __ldg(data + k);
+			for (uint64_t q0 = 0; q0 < limit; q0 += warp_size * ci_unroll) {
+				uint_t<OutputIndexSize> positions[ci_unroll];
+				uint_t<ElementSize> values[ci_unroll];
+				#pragma unroll
+				for (unsigned u = 0; u < ci_unroll; u++) {
+					const uint64_t q = q0 + u * warp_size + lane;
+					if (q < limit) {
+						unsigned r = 0; // the first staged run whose end exceeds q
+						#pragma unroll
+						for (unsigned step = warp_size / 2; step > 0; step >>= 1) { if (staged.ends[r + step - 1] <= q) { r += step; } }
+						const uint64_t j = q - (r == 0 ? 0 : staged.ends[r - 1]);
+						positions[u] = (uint_t<OutputIndexSize>)(staged.baselines[r] +
+							load_offset(scatter_position_offset_bytes + staged.offset_starts[r], j, staged.widths[r]));
+						values[u] = __ldg(data + next_value + q);
+					}
+				}
+				#pragma unroll
+				for (unsigned u = 0; u < ci_unroll; u++) {
+					if (q0 + u * warp_size + lane < limit) { target[positions[u]] = values[u]; }
 				}
 			}
+			next_value += chunk_patches;
 		}
 	}
 }

@@ -437,6 +437,8 @@ def all_cases():
     cases.append(delta_case(10, 1 << 20, 1 << 18, 2, 1))
     cases.append(delta_case(11, 3 << 18, 1 << 18, 8, 1, I=8))
     cases.append(delta_case(12, (1 << 22) + 5, 1 << 21, 8, 2))
+    cases.append(delta_case(13, (1 << 23) + 77, 1 << 23, 4, 1))             # > 1000 tiles in one segment: look-backs of several rounds
+    cases.append(delta_case(14, 3 * 12288 + 100, 12288, 8, 4))              # the shortest segments which take the look-back path
     # Dictionary (20 keys)
     for I in (4, 8):
         for (U, DI) in [(1, 1), (2, 1), (2, 2), (4, 1), (4, 2), (4, 4), (8, 1), (8, 2), (8, 4), (8, 8)]:
@@ -445,6 +447,9 @@ def all_cases():
     cases.append(dictionary_case(2, 1 << 20, 8, 1, 256, cache=False))
     cases.append(dictionary_case(3, 1 << 18, 4, 2, 40000, cache=True))    # 160 KB dictionary in shared memory
     cases.append(dictionary_case(4, 9, 8, 1, 3))
+    cases.append(dictionary_case(5, 1 << 19, 4, 2, 60000, cache=True))    # 240 KB: its head in shared memory, its tail through L1/L2
+    cases.append(dictionary_case(6, 1 << 18, 8, 4, 100000, cache=True))   # 800 KB: mostly through L1/L2
+    cases.append(dictionary_case(7, 1 << 18, 2, 2, 65536, cache=True))    # all 16-bit indices, 128 KB
     # DZB fixed (12 keys)
     for I in (4, 8):
         for (U, C) in [(2, 1), (4, 1), (4, 2), (8, 1), (8, 2), (8, 4)]:
