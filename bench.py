@@ -441,34 +441,33 @@ def run_e2e(args, torch, np, g, columns, kernel, column, out, device, distribute
     dev = {k: torch.empty_like(column[k]) for k in host}  # in-place placement: absolute run indices stay valid
     num_chunks, num_streams, sample_elements = 16, 4, 16384
     chunks = [columns.RunLengthShard(anchors_np, s0, s1, L, n, R) for (s0, s1) in columns.split_segments(S, num_chunks)]
-    streams = [torch.cuda.Stream(device=device) for _ in range(num_streams)]
     samples = torch.empty((num_chunks, sample_elements), dtype=torch.int32).pin_memory()
     h2d_bytes = sum(c.num_runs * 6 + (c.s1 - c.s0) * 6 for c in chunks)
     d2h_bytes = num_chunks * sample_elements * 4
     launches = [0]
 
+    # The plan is built once (host side, untimed) with the library's host-resident scan executor (include/giddy_b200.h
+    # group 4: C++, behind the C ABI); a step replays it: every copy and every launch below is enqueued by the library.
+    scan = kernel._library.create_scan(num_streams)
+    for index, shard in enumerate(chunks):
+        chunk = scan.chunk(index)
+        runs, segments = shard.run_slice(), shard.segment_slice()
+        chunk.copy(dev["run_data"][runs], host["run_data"][runs])
+        chunk.copy(dev["run_lengths"][runs], host["run_lengths"][runs])
+        chunk.copy(dev["position_anchors"][segments], host["position_anchors"][segments])
+        chunk.copy(dev["intra_run_anchor_offsets"][segments], host["intra_run_anchor_offsets"][segments])
+        arguments = rle_arguments(
+            g, column, out.data_ptr() + 4 * shard.first_element, dev["position_anchors"].data_ptr() + 4 * shard.s0,
+            dev["intra_run_anchor_offsets"].data_ptr() + 2 * shard.s0, shard.s1 - shard.s0, shard.num_elements,
+            run_data=dev["run_data"], run_lengths=dev["run_lengths"])
+        config = kernel.resolve_launch_configuration({"length": g.size_t(shard.num_elements), "segment_length": g.size_t(L)})
+        scan.add_launch(index, kernel, config, arguments)
+        tail = shard.first_element + shard.num_elements - sample_elements
+        chunk.copy_back(samples[index], out[tail: tail + sample_elements])
+
     def step():
-        current = torch.cuda.current_stream()
-        for index, shard in enumerate(chunks):
-            stream = streams[index % num_streams]
-            stream.wait_stream(current)
-            with torch.cuda.stream(stream):
-                runs, segments = shard.run_slice(), shard.segment_slice()
-                dev["run_data"][runs].copy_(host["run_data"][runs], non_blocking=True)
-                dev["run_lengths"][runs].copy_(host["run_lengths"][runs], non_blocking=True)
-                dev["position_anchors"][segments].copy_(host["position_anchors"][segments], non_blocking=True)
-                dev["intra_run_anchor_offsets"][segments].copy_(host["intra_run_anchor_offsets"][segments], non_blocking=True)
-                arguments = rle_arguments(
-                    g, column, out.data_ptr() + 4 * shard.first_element, dev["position_anchors"].data_ptr() + 4 * shard.s0,
-                    dev["intra_run_anchor_offsets"].data_ptr() + 2 * shard.s0, shard.s1 - shard.s0, shard.num_elements,
-                    run_data=dev["run_data"], run_lengths=dev["run_lengths"])
-                config = kernel.resolve_launch_configuration({"length": g.size_t(shard.num_elements), "segment_length": g.size_t(L)})
-                kernel.enqueue_launch(stream, config, arguments)
-                launches[0] += 1
-                tail = shard.first_element + shard.num_elements - sample_elements
-                samples[index].copy_(out[tail: tail + sample_elements], non_blocking=True)
-        for stream in streams:
-            current.wait_stream(stream)
+        scan.run()
+        launches[0] += num_chunks
 
     def barrier():
         if distributed:
@@ -502,9 +501,25 @@ def run_e2e(args, torch, np, g, columns, kernel, column, out, device, distribute
               "d2h_bytes_per_step": d2h_bytes, "steps": steps, "ms_per_step": elapsed_ms / steps, "gpu_launches": launches[0],
               "chunks": num_chunks, "streams": num_streams, "sample_matches": ok,
               "what": "pinned host compressed column -> H2D in %d segment-range chunks on %d streams -> decode per chunk -> "
-                      "D2H of each chunk's last %d elements; the decompressed column stays in HBM for its GPU consumer" % (
+                      "D2H of each chunk's last %d elements; the decompressed column stays in HBM for its GPU consumer; "
+                      "planned once and replayed by the library's host-resident scan executor (giddy_scan_run)" % (
                           num_chunks, num_streams, sample_elements),
               "h2d_gbs": h2d_bytes * steps / (elapsed_ms / 1e3) / 1e9}
+    # variant: the same plan replayed as one captured CUDA graph
+    try:
+        scan.set_graph_replay(True)
+        step()
+        torch.cuda.synchronize()
+        s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s1.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        result["with_graph_replay"] = {"value": world * n * 4 * steps / (s1.elapsed_time(e1) / 1e3) / 1e9, "unit": "GB/s", "steps": steps}
+    except Exception as error:
+        result["with_graph_replay"] = {"skipped": str(error)[:100]}
+    scan.set_graph_replay(False)
     # variant: also bring the whole decompressed column back to the host (PCIe-bound on the 4 GiB output)
     try:
         host_out = torch.empty(n, dtype=torch.int32).pin_memory()

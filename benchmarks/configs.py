@@ -495,50 +495,55 @@ def host_resident_scan(args, device, product, rows, n, L, A, K, S_, p, num_runs,
     assert next_period == num_periods
     h2d_bytes = (sum(t.numel() * t.element_size() for d in (host_a, host_b, host_c) for t in d.values()) - host_b["starts"].numel() * 0)
 
-    def copy(dst, src, a, b):
-        dst[a:b].copy_(src[a:b], non_blocking=True)
+    # ---- the plan, recorded once in the library's host-resident scan executor (include/giddy_b200.h group 4) --------
+    # chunk c: side stream c % num_streams; a pass (`step`) is one giddy_scan_run(): every copy and launch is enqueued
+    # by the library, in C++.
+    scan = product.create_scan(num_streams)
+
+    def copy(chunk, dst, src, a, b):
+        if b > a:
+            chunk.copy(dst[a:b], src[a:b])
+
+    for index, plan in enumerate(plans):
+        chunk = scan.chunk(index)
+        (s0, s1), (e0, e1), (k0, k1), (r0, r1), (u0, u1), (q0, q1), (w0, w1) = (plan[x] for x in "sekruqw")
+        # column A: Frame of Reference, then the patches whose periods end in this chunk
+        copy(chunk, dev_a["offsets"], host_a["offsets"], e0, e1)
+        copy(chunk, dev_a["coefficients"], host_a["coefficients"], s0, s1)
+        S.frame_of_reference(out_a[e0:e1], dev_a["offsets"][e0:e1], dev_a["coefficients"][s0:s1], e1 - e0, L, uncompressed_size=4,
+                             compressed_size=2, model="linear", stream=chunk, library=product)
+        if k1 > k0:
+            if index > 0:
+                chunk.after(index - 1)  # the first period may reach back into the previous chunk
+            copy(chunk, dev_a["patch_values"], host_a["patch_values"], q0, q1)
+            for name in ("ci_run_lengths", "ci_offset_sizes", "ci_baselines", "ci_offsets_start"):
+                copy(chunk, dev_a[name], host_a[name], u0, u1)
+            copy(chunk, dev_a["ci_offset_bytes"], host_a["ci_offset_bytes"], *plan["b"])
+            chunk.copy(plan["dev_anchors_a"], plan["host_anchors_a"])
+            S.compressed_indices_scatter(out_a, dev_a["patch_values"][q0:q1], dev_a["ci_run_lengths"][u0:u1], dev_a["ci_offset_sizes"][u0:u1],
+                                         dev_a["ci_baselines"][u0:u1], dev_a["ci_offsets_start"][u0:u1], dev_a["ci_offset_bytes"],
+                                         plan["dev_anchors_a"], A, u1 - u0, q1 - q0, element_size=4, output_index_size=4,
+                                         input_index_size=4, stream=chunk, library=product)
+        # column B: Run-Position Encoding
+        copy(chunk, dev_b["values"], host_b["values"], r0, r1)
+        chunk.copy(dev_b["starts"][r0:r1], plan["host_starts"])
+        chunk.copy(dev_b["anchors"][s0:s1], plan["host_anchors_b"])
+        S.run_position_encoding(out_b[e0:], dev_b["values"][r0:r1], dev_b["starts"][r0:r1], dev_b["anchors"][s0:s1], L, s1 - s0, r1 - r0, e1 - e0,
+                                uncompressed_size=4, position_offset_size=4, relative=False, stream=chunk, library=product)
+        # column C: incidence bitmaps
+        if index == 0:
+            chunk.copy(dev_dictionary, host_c["dictionary"])
+        elif index < num_streams:
+            chunk.after(0)  # (the dictionary arrives with the first chunk)
+        chunk.copy(plan["compact_c"], plan["host_compact_c"])
+        scan.add_launch(index, kernel_c, plan["config_c"], {
+            "decompressed": g.ptr(out_c[e0:e1], "u32"), "incidence_bitmaps": g.cptr(plan["compact_c"], "u32"),
+            "dictionary_entries": g.cptr(dev_dictionary, "u32"), "bitmap_length": g.u32(w1 - w0), "num_bitmaps": g.u32(K)})
+    if args.graph_replay:
+        scan.set_graph_replay(True)
 
     def step():
-        current = torch.cuda.current_stream()
-        for index, plan in enumerate(plans):
-            stream = streams[index % num_streams]
-            stream.wait_stream(current)
-            (s0, s1), (e0, e1), (k0, k1), (r0, r1), (u0, u1), (q0, q1), (w0, w1) = (plan[x] for x in "sekruqw")
-            with torch.cuda.stream(stream):
-                # column A: Frame of Reference, then the patches whose periods end in this chunk
-                copy(dev_a["offsets"], host_a["offsets"], e0, e1)
-                copy(dev_a["coefficients"], host_a["coefficients"], s0, s1)
-                S.frame_of_reference(out_a[e0:e1], dev_a["offsets"][e0:e1], dev_a["coefficients"][s0:s1], e1 - e0, L, uncompressed_size=4,
-                                     compressed_size=2, model="linear", stream=stream, library=product)
-                if k1 > k0:
-                    if index > 0:
-                        stream.wait_stream(streams[(index - 1) % num_streams])  # the first period may reach back into the previous chunk
-                    copy(dev_a["patch_values"], host_a["patch_values"], q0, q1)
-                    for name in ("ci_run_lengths", "ci_offset_sizes", "ci_baselines", "ci_offsets_start"):
-                        copy(dev_a[name], host_a[name], u0, u1)
-                    copy(dev_a["ci_offset_bytes"], host_a["ci_offset_bytes"], *plan["b"])
-                    plan["dev_anchors_a"].copy_(plan["host_anchors_a"], non_blocking=True)
-                    S.compressed_indices_scatter(out_a, dev_a["patch_values"][q0:q1], dev_a["ci_run_lengths"][u0:u1], dev_a["ci_offset_sizes"][u0:u1],
-                                                 dev_a["ci_baselines"][u0:u1], dev_a["ci_offsets_start"][u0:u1], dev_a["ci_offset_bytes"],
-                                                 plan["dev_anchors_a"], A, u1 - u0, q1 - q0, element_size=4, output_index_size=4,
-                                                 input_index_size=4, stream=stream, library=product)
-                # column B: Run-Position Encoding
-                copy(dev_b["values"], host_b["values"], r0, r1)
-                dev_b["starts"][r0:r1].copy_(plan["host_starts"], non_blocking=True)
-                dev_b["anchors"][s0:s1].copy_(plan["host_anchors_b"], non_blocking=True)
-                S.run_position_encoding(out_b[e0:], dev_b["values"][r0:r1], dev_b["starts"][r0:r1], dev_b["anchors"][s0:s1], L, s1 - s0, r1 - r0, e1 - e0,
-                                        uncompressed_size=4, position_offset_size=4, relative=False, stream=stream, library=product)
-                # column C: incidence bitmaps
-                if index == 0:
-                    dev_dictionary.copy_(host_c["dictionary"], non_blocking=True)
-                elif index < num_streams:
-                    stream.wait_stream(streams[0])  # (the dictionary arrives on the first stream)
-                plan["compact_c"].copy_(plan["host_compact_c"], non_blocking=True)
-                kernel_c.enqueue_launch(stream, plan["config_c"], {
-                    "decompressed": g.ptr(out_c[e0:e1], "u32"), "incidence_bitmaps": g.cptr(plan["compact_c"], "u32"),
-                    "dictionary_entries": g.cptr(dev_dictionary, "u32"), "bitmap_length": g.u32(w1 - w0), "num_bitmaps": g.u32(K)})
-        for stream in streams:
-            current.wait_stream(stream)
+        scan.run()
 
     resident_outputs = [o.clone() for o in (out_a, out_b[:n], out_c)]
     for o in (out_a, out_b, out_c):
@@ -551,6 +556,7 @@ def host_resident_scan(args, device, product, rows, n, L, A, K, S_, p, num_runs,
     seconds = time_passes(step, repeats)
     output_bytes = 3 * n * 4
     extra = {"h2d_bytes_per_pass": h2d_bytes, "h2d_gbs_per_gpu": h2d_bytes / seconds / 1e9, "chunks": num_chunks, "streams": num_streams,
+             "executor": "giddy_scan_run (%d recorded operations%s)" % (scan.num_operations, ", replayed as a CUDA graph" if args.graph_replay else ""),
              "compression_ratio": output_bytes / h2d_bytes}
     # the alternative Giddy argues against (README.md:18-24): ship the uncompressed columns over the same link
     raw_host = torch.empty(n, dtype=torch.int32).pin_memory()
@@ -580,6 +586,7 @@ def main():
     parser.add_argument("--repeats", type=int, default=20)
     parser.add_argument("--chunks", type=int, default=16)
     parser.add_argument("--streams", type=int, default=4)
+    parser.add_argument("--graph-replay", action="store_true", help="cfg5 host-resident scan: replay the plan as one captured CUDA graph")
     parser.add_argument("--cfg4-columns", type=int, default=8, help="columns of cfg4 spread over the ranks (1 per GPU at 8 GPUs)")
     parser.add_argument("--no-reference", action="store_true")
     parser.add_argument("--sweep-grids", action="store_true", help="also time the fused patched decoders under several grid sizes")

@@ -416,6 +416,10 @@ GIDDY_API size_t         giddy_scan_num_operations(const giddy_scan_t* scan);
 GIDDY_API giddy_status_t giddy_scan_add_copy(giddy_scan_t* scan, unsigned chunk,
 	void* device_destination, const void* host_source, size_t bytes);
 
+/* The other direction, for (part of) a chunk's result: cudaMemcpyAsync(host_destination, device_source, bytes, DeviceToHost). */
+GIDDY_API giddy_status_t giddy_scan_add_copy_back(giddy_scan_t* scan, unsigned chunk,
+	void* host_destination, const void* device_source, size_t bytes);
+
 /* giddy_kernel_enqueue_launch(kernel, <the chunk's stream>, launch_config, arguments) at this point of the chunk.
  * The argument array is copied; the kernel object must outlive the scan. */
 GIDDY_API giddy_status_t giddy_scan_add_launch(giddy_scan_t* scan, unsigned chunk, const giddy_kernel_t* kernel,

@@ -6,7 +6,7 @@ C++ API: include/giddy/).  This Python package is a thin ctypes binding of the l
 API, used by the test-suite and the benchmark; there is no Python or CPU fallback for any kernel.
 """
 from ._native import (  # noqa: F401
-    Library, Kernel, LaunchConfig, make_launch_config, DeviceProperties, FunctionAttributes,
+    Library, Kernel, Scan, ScanChunk, LaunchConfig, make_launch_config, DeviceProperties, FunctionAttributes,
     b200_device_properties, nominal_function_attributes,
     GiddyError, InvalidArgument, OutOfRange, BadAnyCast, LogicError, CudaError, Unsupported,
     u8, u16, u32, u64, i8, i16, i32, i64, size_t, unsigned, serialization_factor, boolean,

@@ -172,7 +172,28 @@ def load_library(path=_LIB_PATH):
         ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(LaunchConfig), ctypes.POINTER(_Arg), ctypes.c_size_t]
     lib.giddy_device_properties.argtypes = [ctypes.c_int, ctypes.POINTER(DeviceProperties)]
     lib.giddy_function_attributes.argtypes = [ctypes.c_void_p, ctypes.POINTER(FunctionAttributes)]
+    if hasattr(lib, "giddy_scan_create"):  # group 4 (host-resident scans): the product only, not the rebuilt reference
+        lib.giddy_scan_create.argtypes = [ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p)]
+        lib.giddy_scan_destroy.argtypes = [ctypes.c_void_p]
+        lib.giddy_scan_destroy.restype = None
+        for name in ("giddy_scan_num_streams", "giddy_scan_num_chunks"):
+            getattr(lib, name).argtypes = [ctypes.c_void_p]
+            getattr(lib, name).restype = ctypes.c_uint
+        lib.giddy_scan_num_operations.argtypes = [ctypes.c_void_p]
+        lib.giddy_scan_num_operations.restype = ctypes.c_size_t
+        lib.giddy_scan_add_copy.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        lib.giddy_scan_add_copy_back.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        lib.giddy_scan_add_launch.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.POINTER(LaunchConfig),
+                                              ctypes.POINTER(_Arg), ctypes.c_size_t]
+        lib.giddy_scan_add_callback.argtypes = [ctypes.c_void_p, ctypes.c_uint, SCAN_CALLBACK, ctypes.c_void_p, ctypes.c_void_p]
+        lib.giddy_scan_add_dependency.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_uint]
+        lib.giddy_scan_set_graph_replay.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.giddy_scan_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     return lib
+
+
+# giddy_scan_callback_t
+SCAN_CALLBACK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p)
 
 
 class Value:
@@ -324,6 +345,105 @@ class Kernel:
             self._handle, _stream_handle(stream), ctypes.byref(launch_config), array, count))
 
 
+class Scan:
+    """A host-resident scan (include/giddy_b200.h, group 4): a replayable plan of pinned host -> device chunk copies
+    and decode launches on side streams.  Built once, replayed with run().
+
+        scan = library.create_scan(num_streams=4)
+        scan.add_copy(chunk, device_tensor[a:b], pinned_host_tensor[a:b])
+        scan.add_launch(chunk, kernel, config, {"decompressed": ptr(...), ...})
+        scan.add_dependency(chunk, chunk - 1)
+        scan.run()            # asynchronous, on torch's current stream
+    """
+
+    def __init__(self, library, num_streams):
+        self._library = library
+        handle = ctypes.c_void_p()
+        library.check(library.lib.giddy_scan_create(int(num_streams), ctypes.byref(handle)))
+        self._handle = handle
+        self._keepalive = []
+
+    def __del__(self):
+        if getattr(self, "_handle", None):
+            self._library.lib.giddy_scan_destroy(self._handle)
+            self._handle = None
+
+    @property
+    def num_streams(self):
+        return self._library.lib.giddy_scan_num_streams(self._handle)
+
+    @property
+    def num_chunks(self):
+        return self._library.lib.giddy_scan_num_chunks(self._handle)
+
+    @property
+    def num_operations(self):
+        return self._library.lib.giddy_scan_num_operations(self._handle)
+
+    def chunk(self, index):
+        return ScanChunk(self, index)
+
+    def add_copy(self, chunk, destination, source, nbytes=None):
+        """destination: device tensor or address; source: (pinned) host tensor, numpy array or address."""
+        if nbytes is None:
+            nbytes = source.numel() * source.element_size() if hasattr(source, "numel") else source.nbytes
+            if hasattr(destination, "numel") and destination.numel() * destination.element_size() != nbytes:
+                raise ValueError("source and destination of a scan copy differ in size")
+        self._keepalive.append((destination, source))
+        self._library.check(self._library.lib.giddy_scan_add_copy(self._handle, int(chunk), _address_of(destination), _address_of(source), int(nbytes)))
+
+    def add_copy_back(self, chunk, destination, source, nbytes=None):
+        """destination: (pinned) host tensor or address; source: device tensor or address."""
+        if nbytes is None:
+            nbytes = source.numel() * source.element_size()
+        self._keepalive.append((destination, source))
+        self._library.check(self._library.lib.giddy_scan_add_copy_back(self._handle, int(chunk), _address_of(destination), _address_of(source), int(nbytes)))
+
+    def add_launch(self, chunk, kernel, launch_config, arguments):
+        array, count, names = _marshal(arguments)
+        self._keepalive.append((kernel, [v.keepalive for v in arguments.values()]))
+        self._library.check(self._library.lib.giddy_scan_add_launch(self._handle, int(chunk), kernel._handle, ctypes.byref(launch_config), array, count))
+
+    def add_callback(self, chunk, enqueue):
+        """enqueue(stream_handle) is called at every replay and must only enqueue asynchronous work on that stream."""
+        def trampoline(stream, _user_data):
+            try:
+                enqueue(stream)
+                return 0
+            except Exception:
+                return 7
+        callback = SCAN_CALLBACK(trampoline)
+        self._keepalive.append((callback, enqueue))
+        self._library.check(self._library.lib.giddy_scan_add_callback(self._handle, int(chunk), callback, None, None))
+
+    def add_dependency(self, chunk, on_chunk):
+        self._library.check(self._library.lib.giddy_scan_add_dependency(self._handle, int(chunk), int(on_chunk)))
+
+    def set_graph_replay(self, enabled=True):
+        self._library.check(self._library.lib.giddy_scan_set_graph_replay(self._handle, 1 if enabled else 0))
+
+    def run(self, stream=None):
+        self._library.check(self._library.lib.giddy_scan_run(self._handle, _stream_handle(stream)))
+
+
+class ScanChunk:
+    """One chunk of a scan under construction.  Passed as the `stream` of a libgiddy_b200.schemes launch helper, it
+    records the launch in the scan instead of enqueueing it."""
+    __slots__ = ("scan", "index")
+
+    def __init__(self, scan, index):
+        self.scan, self.index = scan, int(index)
+
+    def copy(self, destination, source, nbytes=None):
+        self.scan.add_copy(self.index, destination, source, nbytes)
+
+    def copy_back(self, destination, source, nbytes=None):
+        self.scan.add_copy_back(self.index, destination, source, nbytes)
+
+    def after(self, on_chunk):
+        self.scan.add_dependency(self.index, on_chunk.index if isinstance(on_chunk, ScanChunk) else on_chunk)
+
+
 class Library:
     """One loaded shared library exporting the registry API (the product, or the rebuilt reference)."""
 
@@ -349,6 +469,9 @@ class Library:
         handle = ctypes.c_void_p()
         self.check(self.lib.giddy_produce_subclass(key.encode(), ctypes.byref(handle)))
         return Kernel(self, handle)
+
+    def create_scan(self, num_streams=4):
+        return Scan(self, num_streams)
 
     def device_properties(self, device_id=-1):
         p = DeviceProperties()

@@ -28,7 +28,7 @@ using giddy::abi::fail;
 using giddy::abi::fail_cuda;
 
 struct operation_t {
-	enum kind_t { copy, launch, callback, record, wait } kind;
+	enum kind_t { copy, copy_back, launch, callback, record, wait } kind;
 	// copy
 	void* destination = nullptr; const void* source = nullptr; size_t bytes = 0;
 	// launch: a deep copy of the caller's argument array
@@ -95,6 +95,10 @@ struct giddy_scan {
 				case operation_t::copy:
 					error = cudaMemcpyAsync(op.destination, op.source, op.bytes, cudaMemcpyHostToDevice, stream);
 					if (error != cudaSuccess) { return fail_cuda(error, "cudaMemcpyAsync (scan chunk copy)"); }
+					break;
+				case operation_t::copy_back:
+					error = cudaMemcpyAsync(op.destination, op.source, op.bytes, cudaMemcpyDeviceToHost, stream);
+					if (error != cudaSuccess) { return fail_cuda(error, "cudaMemcpyAsync (scan result copy)"); }
 					break;
 				case operation_t::launch:
 					status = giddy_kernel_enqueue_launch(op.kernel, stream, &op.config, op.arguments.data(), op.arguments.size());
@@ -167,6 +171,17 @@ giddy_status_t giddy_scan_add_copy(giddy_scan_t* scan, unsigned chunk, void* dev
 	if (device_destination == nullptr || host_source == nullptr) { return fail(GIDDY_INVALID_ARGUMENT, "null copy source or destination"); }
 	operation_t op; op.kind = operation_t::copy;
 	op.destination = device_destination; op.source = host_source; op.bytes = bytes;
+	scan->chunk(chunk).push_back(::std::move(op));
+	return GIDDY_SUCCESS;
+}
+
+giddy_status_t giddy_scan_add_copy_back(giddy_scan_t* scan, unsigned chunk, void* host_destination, const void* device_source, size_t bytes)
+{
+	if (scan == nullptr) { return fail(GIDDY_INVALID_ARGUMENT, "null scan"); }
+	if (bytes == 0) { return GIDDY_SUCCESS; }
+	if (host_destination == nullptr || device_source == nullptr) { return fail(GIDDY_INVALID_ARGUMENT, "null copy source or destination"); }
+	operation_t op; op.kind = operation_t::copy_back;
+	op.destination = host_destination; op.source = device_source; op.bytes = bytes;
 	scan->chunk(chunk).push_back(::std::move(op));
 	return GIDDY_SUCCESS;
 }

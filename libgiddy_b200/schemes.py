@@ -46,7 +46,10 @@ def _run(library, key, resolve_arguments, launch_arguments, stream, limits, devi
         if len(_configurations) > 4096:
             _configurations.clear()
         _configurations[signature] = config
-    kernel.enqueue_launch(stream, config, launch_arguments)
+    if isinstance(stream, N.ScanChunk):  # building a host-resident scan: record the launch instead of enqueueing it
+        stream.scan.add_launch(stream.index, kernel, config, launch_arguments)
+    else:
+        kernel.enqueue_launch(stream, config, launch_arguments)
     return config
 
 
