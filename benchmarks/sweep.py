@@ -55,6 +55,8 @@ def workloads(log2_n):
     w.append(("cfg5 Incidence bitmaps u32 K=16", lambda: cases.bitmaps_case(1, n, 4, 16)))
     w.append(("cfg3 scatter u64 1% patches", lambda: cases.scatter_case(1, n // 2, n // 200, 8, 4, 4)))
     w.append(("cfg3 fused patched Dictionary u64<-u8 1%", lambda: cases.patched_dictionary_case(1, n // 2, 8, 1, 256, n // 200)))
+    w.append(("diagnostic: patched Dictionary u64<-u8, no patches", lambda: cases.patched_dictionary_case(1, n // 2, 8, 1, 256, 0)))
+    w.append(("diagnostic: patched Dictionary u64<-u8, 0.01% patches", lambda: cases.patched_dictionary_case(1, n // 2, 8, 1, 256, n // 20000)))
     w.append(("fused patched Dictionary u32<-u8 5%", lambda: cases.patched_dictionary_case(1, n, 4, 1, 256, n // 20)))
     w.append(("cfg5 fused patched FOR i32<-i16 linear ci 1%", lambda: cases.patched_for_case(1, n, 1024, 4, 2, "linear", n // 100, 1024)))
     w.append(("cfg5 ci-scatter u32 1% patches A=1024", lambda: cases.ci_scatter_case(1, n, n // 100, 4, 4, 4, 1024)))

@@ -56,13 +56,10 @@
 	((segment_length) >= 2 * GIDDY_DELTA_TILE_ELEMENTS(U, GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS) && \
 	 ((length) + (segment_length) - 1) / (segment_length) < 8192)
 
-/* Patched decoders (decode + patches in one pass): every warp owns a contiguous range of warp tiles (32 x
- * GIDDY_ELEMENTWISE_UNROLL vectors each); CTAs of at most this many threads; this many CTAs per multiprocessor are
- * asked for (several waves, so that each warp's one-off patch seek and the last wave's imbalance stay small against
- * its streaming work); compressed patch positions are decoded this many at a time into each warp's slice of (static)
- * shared memory. */
-#define GIDDY_PATCHED_BLOCK_THREADS 256
-#define GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR 32
-#define GIDDY_PATCHED_WINDOW 128
+/* Patched decoders (decode + patches in one pass): warp tiles of 32 x this many output vectors go grid-stride to the
+ * warps of this many CTAs (of GIDDY_ELEMENTWISE_BLOCK_THREADS threads) per multiprocessor; an index of one patch range per
+ * tile is built into a workspace before the decode. */
+#define GIDDY_PATCHED_UNROLL 8
+#define GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR 5
 
 #endif /* GIDDY_KERNEL_TRAITS_H_ */

@@ -942,20 +942,22 @@ const device_function_t kernel_t<I, U, C, CS>::get_device_function() const
 
 namespace detail_patched {
 
-/// The launch-configuration policy shared by the patched decoders: block resolution, CTAs of GIDDY_PATCHED_BLOCK_THREADS
-/// threads each owning a contiguous range of tiles, GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR of them per multiprocessor
-/// (fewer when the column has fewer tiles).  The kernels are correct under any grid and any whole-warp block.
+/// The launch-configuration policy shared by the patched decoders: warp tiles of 32 x GIDDY_PATCHED_UNROLL output vectors,
+/// handed grid-stride to the warps of a grid of GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR CTAs of GIDDY_ELEMENTWISE_BLOCK_
+/// THREADS threads per multiprocessor (fewer when the column is short), so that a warp decodes several tiles and can
+/// request a tile's patch range an iteration ahead.  The kernels are correct under any grid and any whole-warp block
+/// up to that size.
 inline void configure(launch_config_resolution_params_t& p, ::std::size_t length_in_elements, unsigned uncompressed_size)
 {
-	const ::std::size_t elements_per_tile = (::std::size_t) GIDDY_PATCHED_BLOCK_THREADS * GIDDY_ELEMENTWISE_UNROLL * (16 / uncompressed_size);
+	const ::std::size_t elements_per_block_tile = (::std::size_t) GIDDY_ELEMENTWISE_BLOCK_THREADS * GIDDY_PATCHED_UNROLL * (16 / uncompressed_size);
 	p.grid_construction_resolution  = launch_config_resolution_params_t::block;
 	p.serialization_option          = launch_config_resolution_params_t::auto_maximized;
-	p.length                        = util::div_rounding_up(length_in_elements, elements_per_tile);
+	p.length                        = util::div_rounding_up(length_in_elements, elements_per_block_tile);
 	p.quanta.threads_in_block       = warp_size;
-	p.upper_limits.threads_in_block = GIDDY_PATCHED_BLOCK_THREADS;
-	p.block_resolution_constraints.max_threads_per_block = GIDDY_PATCHED_BLOCK_THREADS;
+	p.upper_limits.threads_in_block = GIDDY_ELEMENTWISE_BLOCK_THREADS;
+	p.block_resolution_constraints.max_threads_per_block = GIDDY_ELEMENTWISE_BLOCK_THREADS;
 	// blocks = multiprocessors x warp schedulers (4) x factor / warps per block
-	p.keep_gpu_busy_factor          = GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR * (GIDDY_PATCHED_BLOCK_THREADS / warp_size) / 4;
+	p.keep_gpu_busy_factor          = GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR * (GIDDY_ELEMENTWISE_BLOCK_THREADS / warp_size) / 4;
 }
 
 } // namespace detail_patched

@@ -20,6 +20,41 @@ giddy_status_t fail_cuda(cudaError_t error, const char* what)
 	return fail(GIDDY_CUDA_ERROR, std::string(what) + ": " + cudaGetErrorName(error) + " (" + cudaGetErrorString(error) + ")");
 }
 
+// Workspaces (the Delta look-back's tile descriptors, the patched decoders' tile index) come from a pool of this
+// library's own, one per device, which keeps what it has been given (release threshold: never): the default pool hands
+// its memory back to the driver at every synchronisation, and the next launch then pays for mapping it again.
+static cudaError_t workspace_pool(cudaMemPool_t* pool)
+{
+	static std::mutex guard;
+	static cudaMemPool_t pools[64] = { };
+	int device = 0;
+	cudaError_t error = cudaGetDevice(&device);
+	if (error != cudaSuccess) { return error; }
+	if (device < 0 || device >= 64) { return cudaDeviceGetDefaultMemPool(pool, device); }
+	std::lock_guard<std::mutex> lock(guard);
+	if (pools[device] == nullptr) {
+		cudaMemPoolProps properties = { };
+		properties.allocType = cudaMemAllocationTypePinned;
+		properties.handleTypes = cudaMemHandleTypeNone;
+		properties.location.type = cudaMemLocationTypeDevice;
+		properties.location.id = device;
+		error = cudaMemPoolCreate(&pools[device], &properties);
+		if (error != cudaSuccess) { pools[device] = nullptr; return error; }
+		unsigned long long keep = ~0ull;
+		cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+	}
+	*pool = pools[device];
+	return cudaSuccess;
+}
+
+cudaError_t allocate_workspace(void** workspace, size_t bytes, cudaStream_t stream)
+{
+	cudaMemPool_t pool = nullptr;
+	cudaError_t error = workspace_pool(&pool);
+	if (error != cudaSuccess) { return error; }
+	return cudaMallocFromPoolAsync(workspace, bytes, pool, stream);
+}
+
 } // namespace abi
 } // namespace giddy
 

@@ -1,6 +1,5 @@
 // C ABI launcher for the Delta decoder (include/giddy_b200.h, kernel API).
 // Instantiations: src/kernel_wrappers/decompression/delta.cu:94-106.
-#include <mutex>
 #include "abi_internal.hpp"
 #include "../kernels/delta.cuh"
 
@@ -20,33 +19,6 @@ giddy_status_t delta_launch(void* stream, const giddy_launch_config_t* cfg, void
 		static_cast<uint_t<U>*>(out), static_cast<const uint_t<C>*>(in), static_cast<const uint_t<U>*>(anchors),
 		(size_type<I>) n, (size_type<I>) L);
 }
-// The look-back workspace comes from a pool of this library's own, one per device, which keeps what it has been given
-// (release threshold: never): the default pool hands its memory back to the driver at every synchronisation, and the
-// next launch then pays for mapping it again.
-cudaError_t workspace_pool(cudaMemPool_t* pool)
-{
-	static std::mutex guard;
-	static cudaMemPool_t pools[64] = { };
-	int device = 0;
-	cudaError_t error = cudaGetDevice(&device);
-	if (error != cudaSuccess) { return error; }
-	if (device < 0 || device >= 64) { return cudaDeviceGetDefaultMemPool(pool, device); }
-	std::lock_guard<std::mutex> lock(guard);
-	if (pools[device] == nullptr) {
-		cudaMemPoolProps properties = { };
-		properties.allocType = cudaMemAllocationTypePinned;
-		properties.handleTypes = cudaMemHandleTypeNone;
-		properties.location.type = cudaMemLocationTypeDevice;
-		properties.location.id = device;
-		error = cudaMemPoolCreate(&pools[device], &properties);
-		if (error != cudaSuccess) { pools[device] = nullptr; return error; }
-		unsigned long long keep = ~0ull;
-		cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
-	}
-	*pool = pools[device];
-	return cudaSuccess;
-}
-
 // Whether grids can be launched cooperatively on the current device (all CTAs resident at once).
 bool cooperative_launch_supported()
 {
@@ -71,13 +43,14 @@ giddy_status_t delta_long_launch(void* stream, const giddy_launch_config_t* cfg,
 		int device = 0, multiprocessors = 0, per_multiprocessor = 0;
 		cudaError_t error = cudaGetDevice(&device);
 		if (error == cudaSuccess) { error = cudaDeviceGetAttribute(&multiprocessors, cudaDevAttrMultiProcessorCount, device); }
-		if (error == cudaSuccess) { error = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_multiprocessor, kernel, (int) cfg->block_dimensions[0], 0); }
+		const unsigned block = cfg->block_dimensions[0];
+		if (error == cudaSuccess) { error = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_multiprocessor, kernel, (int) block, 0); }
 		if (error != cudaSuccess) { return fail_cuda(error, "occupancy query (Delta look-back)"); }
 		const unsigned resident = (unsigned) multiprocessors * (unsigned) per_multiprocessor;
 		if (resident > 0) {
 			const unsigned grid = cfg->grid_dimensions[0] < resident ? cfg->grid_dimensions[0] : resident;
 			void* arguments[] = { &out_, &in_, &anchors_, &n_, &L_, &workspace };
-			error = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(cfg->block_dimensions[0]), arguments, 0,
+			error = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(block), arguments, 0,
 				static_cast<cudaStream_t>(stream));
 			if (error != cudaSuccess) { return fail_cuda(error, "cooperative kernel launch (Delta look-back)"); }
 			return GIDDY_SUCCESS;
@@ -134,9 +107,7 @@ extern "C" giddy_status_t giddy_b200_delta_launch(
 	const size_t workspace_bytes = 32 + (size_t) num_tiles * 16;
 	void* workspace = nullptr;
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
-	cudaMemPool_t pool = nullptr;
-	cudaError_t error = workspace_pool(&pool);
-	if (error == cudaSuccess) { error = cudaMallocFromPoolAsync(&workspace, workspace_bytes, pool, s); }
+	cudaError_t error = allocate_workspace(&workspace, workspace_bytes, s);
 	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocFromPoolAsync (Delta look-back workspace)"); }
 	error = cudaMemsetAsync(workspace, 0, workspace_bytes, s);
 	if (error != cudaSuccess) { cudaFreeAsync(workspace, s); return fail_cuda(error, "cudaMemsetAsync (Delta look-back workspace)"); }

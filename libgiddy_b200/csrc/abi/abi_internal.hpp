@@ -15,6 +15,10 @@ namespace abi {
 giddy_status_t fail(giddy_status_t status, const std::string& message);
 giddy_status_t fail_cuda(cudaError_t error, const char* what);
 
+// Stream-ordered scratch memory for the duration of a launch, from the library's own pool (abi_common.cu); release with
+// cudaFreeAsync on the same stream.
+cudaError_t allocate_workspace(void** workspace, size_t bytes, cudaStream_t stream);
+
 inline dim3 to_dim3(const unsigned (&d)[3]) { return dim3(d[0], d[1] ? d[1] : 1, d[2] ? d[2] : 1); }
 
 // Kernels which want more than the default 48 KiB of dynamic shared memory must opt in once per

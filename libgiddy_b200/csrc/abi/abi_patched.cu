@@ -14,14 +14,58 @@ using dict_launcher_t = giddy_status_t (*)(void*, const giddy_launch_config_t*, 
 	const void*, const void*, uint64_t);
 struct dict_entry_t { unsigned I, U, DI; const void* kernel; dict_launcher_t launch; };
 
+// The tile index (kernels/patched.cuh): log2 of the warp tile's element count for this pair of buffers, and the launch
+// of patch_tile_ranges into `ranges` (num_tiles entries).
+template <unsigned U>
+unsigned log2_tile_elements(const void* decompressed, const void* compressed_input, unsigned compressed_element_size)
+{
+	constexpr unsigned E = 16 / U;
+	const bool vectorizable = reinterpret_cast<uintptr_t>(decompressed) % 16 == 0 &&
+		reinterpret_cast<uintptr_t>(compressed_input) % (E * compressed_element_size) == 0;
+	unsigned elements = 32 * GIDDY_PATCHED_UNROLL * (vectorizable ? E : 1), log2 = 0;
+	while ((1u << log2) < elements) { log2++; }
+	return log2;
+}
+
+template <unsigned I>
+size_t tile_index_bytes(uint64_t num_tiles) { return (size_t) num_tiles * sizeof(kernels::patched_detail::patch_range_t<I>); }
+
+template <unsigned I>
+giddy_status_t build_tile_index(cudaStream_t stream, void* ranges, const void* positions, uint64_t num_patches, unsigned log2_tile, uint64_t num_tiles)
+{
+	cudaError_t error = cudaMemsetAsync(ranges, 0, tile_index_bytes<I>(num_tiles), stream);
+	if (error != cudaSuccess) { return fail_cuda(error, "cudaMemsetAsync (patch tile index)"); }
+	if (num_patches == 0) { return GIDDY_SUCCESS; }
+	const unsigned threads = 256;
+	const uint64_t blocks = (num_patches + threads - 1) / threads;
+	kernels::patched_detail::patch_tile_ranges<I><<<(unsigned) (blocks < 0x7fffffffull ? blocks : 0x7fffffffull), threads, 0, stream>>>(
+		static_cast<kernels::patched_detail::patch_range_t<I>*>(ranges), static_cast<const uint_t<I>*>(positions), (size_type<I>) num_patches, log2_tile, num_tiles);
+	error = cudaGetLastError();
+	if (error != cudaSuccess) { return fail_cuda(error, "kernel launch (patch tile index)"); }
+	return GIDDY_SUCCESS;
+}
+
 template <unsigned I, unsigned U, unsigned DI>
 giddy_status_t dict_launch(void* stream, const giddy_launch_config_t* cfg, void* out, const void* in, const void* dict,
 	uint64_t n, uint64_t num_entries, bool cache, const void* patch_data, const void* patch_indices, uint64_t num_patches)
 {
-	return launch(kernels::patched_dictionary_decompress<I, U, DI>, stream, cfg,
-		static_cast<uint_t<U>*>(out), static_cast<const uint_t<DI>*>(in), static_cast<const uint_t<U>*>(dict),
-		(size_type<I>) n, (size_type<DI>) num_entries, cache,
-		static_cast<const uint_t<U>*>(patch_data), static_cast<const uint_t<I>*>(patch_indices), (size_type<I>) num_patches);
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	const unsigned log2_tile = log2_tile_elements<U>(out, in, DI);
+	const uint64_t num_tiles = (n + (1ull << log2_tile) - 1) >> log2_tile;
+	void* offsets = nullptr;
+	cudaError_t error = allocate_workspace(&offsets, tile_index_bytes<I>(num_tiles) + 16, s);
+	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocFromPoolAsync (patch tile index)"); }
+	giddy_status_t status = build_tile_index<I>(s, offsets, patch_indices, num_patches, log2_tile, num_tiles);
+	if (status == GIDDY_SUCCESS) {
+		status = launch(kernels::patched_dictionary_decompress<I, U, DI>, stream, cfg,
+			static_cast<uint_t<U>*>(out), static_cast<const uint_t<DI>*>(in), static_cast<const uint_t<U>*>(dict),
+			(size_type<I>) n, (size_type<DI>) num_entries, cache,
+			static_cast<const uint_t<U>*>(patch_data), static_cast<const uint_t<I>*>(patch_indices),
+			static_cast<const kernels::patched_detail::patch_range_t<I>*>(offsets), log2_tile);
+	}
+	error = cudaFreeAsync(offsets, s);
+	if (status == GIDDY_SUCCESS && error != cudaSuccess) { return fail_cuda(error, "cudaFreeAsync (patch tile index)"); }
+	return status;
 }
 #define DICT_ENTRY(I, U, DI) { I, U, DI, reinterpret_cast<const void*>(&kernels::patched_dictionary_decompress<I, U, DI>), &dict_launch<I, U, DI> }
 
@@ -47,16 +91,41 @@ giddy_status_t for_launch(void* stream, const giddy_launch_config_t* cfg, void* 
 	const void* data, const void* run_lengths, const void* offset_sizes, const void* baselines, const void* offsets_start,
 	const void* offset_bytes, const void* anchors, uint64_t anchoring_period, uint64_t num_runs, uint64_t data_length)
 {
-	return launch(kernels::patched_frame_of_reference_decompress<I, U, C, M, MI, II>, stream, cfg,
-		static_cast<uint_t<U>*>(out), static_cast<const int_t<C>*>(in), static_cast<const int32_t*>(coeffs),
-		(size_type<I>) n, (size_type<I>) L,
-		static_cast<const uint_t<U>*>(data), static_cast<const uint_t<II>*>(run_lengths), static_cast<const unsigned char*>(offset_sizes),
-		static_cast<const uint_t<I>*>(baselines), static_cast<const uint_t<II>*>(offsets_start),
-		static_cast<const unsigned char*>(offset_bytes), static_cast<const uint_t<II>*>(anchors),
-		(uint_t<II>) anchoring_period, (uint_t<II>) num_runs, (size_type<II>) data_length);
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	const unsigned log2_tile = log2_tile_elements<U>(out, in, C);
+	const uint64_t num_tiles = (n + (1ull << log2_tile) - 1) >> log2_tile;
+	// workspace: the tile index, then the decoded patch positions
+	const size_t offsets_bytes = (tile_index_bytes<I>(num_tiles) + 15) / 16 * 16;
+	void* workspace = nullptr;
+	cudaError_t error = allocate_workspace(&workspace, offsets_bytes + data_length * I + 16, s);
+	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocFromPoolAsync (patch positions and tile index)"); }
+	void* positions = static_cast<unsigned char*>(workspace) + offsets_bytes;
+	giddy_status_t status = GIDDY_SUCCESS;
+	if (data_length != 0) {
+		const uint64_t periods = (data_length + anchoring_period - 1) / anchoring_period;
+		const unsigned warps_per_block = GIDDY_CI_SCATTER_WARPS_PER_BLOCK;
+		const uint64_t blocks = (periods + warps_per_block - 1) / warps_per_block;
+		kernels::expand_compressed_indices<I, II, II><<<(unsigned) (blocks < 0x7fffffffull ? blocks : 0x7fffffffull), warps_per_block * 32, 0, s>>>(
+			static_cast<uint_t<I>*>(positions), static_cast<const uint_t<II>*>(run_lengths), static_cast<const unsigned char*>(offset_sizes),
+			static_cast<const uint_t<I>*>(baselines), static_cast<const uint_t<II>*>(offsets_start),
+			static_cast<const unsigned char*>(offset_bytes), static_cast<const uint_t<II>*>(anchors),
+			(uint_t<II>) anchoring_period, (uint_t<II>) num_runs, (size_type<II>) data_length);
+		error = cudaGetLastError();
+		if (error != cudaSuccess) { status = fail_cuda(error, "kernel launch (patch position decode)"); }
+	}
+	if (status == GIDDY_SUCCESS) { status = build_tile_index<I>(s, workspace, positions, data_length, log2_tile, num_tiles); }
+	if (status == GIDDY_SUCCESS) {
+		status = launch(kernels::patched_frame_of_reference_decompress<I, U, C, M, MI>, stream, cfg,
+			static_cast<uint_t<U>*>(out), static_cast<const int_t<C>*>(in), static_cast<const int32_t*>(coeffs),
+			(size_type<I>) n, (size_type<I>) L,
+			static_cast<const uint_t<U>*>(data), static_cast<const uint_t<I>*>(positions), static_cast<const kernels::patched_detail::patch_range_t<I>*>(workspace), log2_tile);
+	}
+	error = cudaFreeAsync(workspace, s);
+	if (status == GIDDY_SUCCESS && error != cudaSuccess) { return fail_cuda(error, "cudaFreeAsync (patch positions and tile index)"); }
+	return status;
 }
 #define FOR_ENTRY(I, U, C, M, MI, II) { I, U, C, M, MI, II, \
-	reinterpret_cast<const void*>(&kernels::patched_frame_of_reference_decompress<I, U, C, M, MI, II>), &for_launch<I, U, C, M, MI, II> }
+	reinterpret_cast<const void*>(&kernels::patched_frame_of_reference_decompress<I, U, C, M, MI>), &for_launch<I, U, C, M, MI, II> }
 
 const for_entry_t for_table[] = {
 	FOR_ENTRY(4, 2, 1, model_linear,   4, 4), FOR_ENTRY(4, 4, 1, model_linear,   4, 4), FOR_ENTRY(4, 4, 2, model_linear,   4, 4),
@@ -72,7 +141,7 @@ const for_entry_t* find_for(unsigned I, unsigned U, unsigned C, int model, unsig
 
 giddy_status_t check_block(const giddy_launch_config_t* config)
 {
-	if (config->block_dimensions[0] % 32 != 0 || config->block_dimensions[0] == 0 || config->block_dimensions[0] > GIDDY_PATCHED_BLOCK_THREADS) {
+	if (config->block_dimensions[0] % 32 != 0 || config->block_dimensions[0] == 0 || config->block_dimensions[0] > GIDDY_ELEMENTWISE_BLOCK_THREADS) {
 		return fail(GIDDY_INVALID_ARGUMENT, "blocks must be made of 1 to 8 whole warps");
 	}
 	return GIDDY_SUCCESS;

@@ -1,28 +1,34 @@
 // Patched decoders: a position-aligned decoder (Dictionary, Frame of Reference) and its a-posteriori
-// patches applied in ONE pass.
+// patches applied in ONE pass over the column.
 //
 // The reference patches a decompressed column with a second kernel (README.md:55-60): scatter
 // (src/kernels/data_layout/scatter.cuh:26-46) or compressed-indices scatter
 // (src/kernels/data_layout/compressed_indices_scatter.cuh:219-271).  Run on its own, a patch store
 // dirties 4-8 bytes of a 32-byte sector somewhere in a multi-GB column: HBM has to read and rewrite
-// the whole sector (measured: 32 + 32 bytes of DRAM traffic per patch), and both the reference's kernels
-// and this library's stand-alone ones top out at the same ~23 G patches/s.  Here the patch is stored
-// right after the vectors which contain it, by the same warp, while those lines are still dirty in L2 --
-// the patch merges there and costs no HBM access of its own (measured: DRAM traffic = algorithmic bytes).
+// the whole sector (measured: 32 + 32 bytes of DRAM traffic per patch), and random sectors come at ~25 G/s
+// whatever the kernel does.  Storing the patch right after the vector which contains it, while the line is still
+// dirty in L2, saves the HBM traffic (measured: DRAM bytes = algorithmic bytes) but not the time: a partial-sector
+// write still costs L2 a read-modify-write, and three different kernel structures all ended at ~30 G patches/s.
+// Here a tile is therefore patched BEFORE it is stored, in the warp's slice of shared memory, and leaves the SM
+// as whole 16-byte vectors only.
 //
 // Requirement (the only one beyond the two schemes' own): patch positions are in ASCENDING order, as a
 // compressor which emits exceptions while scanning the column produces them.
 //
-// Decomposition: the output is cut into warp tiles of 32 * unroll vectors; every WARP owns a contiguous
-// range of them and is an independent stream processor -- no CTA-wide barrier in the loop.  It seeks its
-// first patch once, with a warp-wide 32-ary search (5 rounds for 5 M patches), and from then on walks the
-// patch stream in step with its tiles:
-//     request the NEXT tile's compressed bytes (software pipelining: two tiles of loads in flight per warp)
-//     decode and store this tile's vectors
-//     __syncwarp (orders those stores before the patch stores), ballot the candidates which fall inside
-//     the tile, store them
-// The candidate patches live in registers (index list: one candidate per lane, reloaded when all 32 are
-// spent) or in a per-warp shared-memory window (compressed indices: 128 decoded positions).
+// Decomposition: the output is cut into warp tiles of 32 x GIDDY_PATCHED_UNROLL vectors, handed grid-stride to the
+// warps of a grid of GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR CTAs per multiprocessor.  What a warp needs to know is
+// which patches fall into its tile; that comes from a small index built just before, in stream order, into a
+// workspace the launcher takes from the library's pool for the duration of the call:
+//     (compressed positions only)  expand_compressed_indices: the run-compressed positions as a plain list
+//     patch_tile_ranges: for every tile with patches, the range of the patch list which falls into it (one
+//                        thread per patch, no loops, no search: a patch opens / closes its tile's range if its
+//                        neighbour in the list lies in another tile; the array starts out zeroed)
+// -- 8 bytes per tile (0.2-0.4 % of the output) plus, for compressed positions, 4 bytes per patch.  The decode
+// kernel then, per tile: (has its range, requested an iteration ahead) requests its compressed vectors and (lane l)
+// patch first + l, decodes the vectors into the warp's 4 KiB of shared memory, overwrites the patched elements
+// there, and stores whole vectors.  A tile without patches is stored straight from registers.
+// (A CTA-tile variant -- the stand-alone decoders' structure with a 16 KiB staging buffer and two barriers per
+// tile -- measured slower: profiles/patched_r01_notes.md.)
 #pragma once
 #ifndef GIDDY_B200_KERNELS_PATCHED_CUH_
 #define GIDDY_B200_KERNELS_PATCHED_CUH_
@@ -35,233 +41,8 @@ namespace kernels {
 
 namespace patched_detail {
 
-constexpr unsigned unroll = GIDDY_ELEMENTWISE_UNROLL;
-constexpr unsigned max_warps_per_block = GIDDY_PATCHED_BLOCK_THREADS / 32;
-constexpr unsigned window_patches = GIDDY_PATCHED_WINDOW;       // decoded patch positions held in shared memory, per warp
-
-// The smallest i in [0, count) with key(i) >= target, or count; key must be non-decreasing.
-// Called by a whole warp with the same arguments.
-template <typename KeyFunction>
-__device__ __forceinline__ uint64_t warp_lower_bound(uint64_t count, uint64_t target, KeyFunction key)
-{
-	uint64_t lo = 0, hi = count; // the answer is in [lo, hi]
-	while (lo < hi) {
-		const uint64_t step = (hi - lo + warp_size - 1) / warp_size;
-		const uint64_t pivot = lo + ((uint64_t) lane_index() + 1) * step - 1;
-		const bool below = pivot < hi && key(pivot) < target;
-		const uint64_t num_below = __popc(__ballot_sync(full_mask, below)); // keys are sorted: the pivots below the target are a prefix
-		const uint64_t past_pivot = lo + (num_below + 1) * step - 1;
-		lo += num_below * step;
-		hi = minimum(hi, past_pivot);
-	}
-	return lo;
-}
-
-__device__ __forceinline__ uint64_t warp_sum(uint64_t x)
-{
-	#pragma unroll
-	for (unsigned d = warp_size / 2; d > 0; d >>= 1) { x += __shfl_xor_sync(full_mask, (unsigned long long) x, d); }
-	return x;
-}
-
-// ---- patch sources ---------------------------------------------------------------------------------
-
-// Patches as a plain list: positions indices[i] (ascending), values data[i]; the arguments of scatter::scatter.
-// Lane l holds candidate window_base + l; a second window is already on its way when the first runs out.
-template <unsigned IndexSize, unsigned U>
-struct index_list_patches {
-	struct shared_t { };
-	const uint_t<U>*          __restrict__ data;
-	const uint_t<IndexSize>*  __restrict__ indices;
-	uint64_t                               count;
-
-	uint64_t           window_base;  // index of lane 0's candidate
-	unsigned           spent;        // the window's candidates already applied: lanes [0, spent)
-	uint_t<IndexSize>  position, next_position;
-	uint_t<U>          value, next_value;
-
-	__device__ __forceinline__ void load_next_window()
-	{
-		const uint64_t i = window_base + warp_size + lane_index();
-		if (i < count) { next_position = __ldg(indices + i); next_value = __ldg(data + i); }
-	}
-
-	__device__ __forceinline__ void seek(uint64_t first_position, shared_t&)
-	{
-		window_base = 0;
-		if (first_position != 0 && count != 0) {
-			window_base = warp_lower_bound(count, first_position, [&](uint64_t i) { return (uint64_t) __ldg(indices + i); });
-		}
-		spent = 0;
-		const uint64_t i = window_base + lane_index();
-		if (i < count) { position = __ldg(indices + i); value = __ldg(data + i); }
-		load_next_window();
-	}
-
-	__device__ __forceinline__ void prefetch() { }
-
-	// Called by the whole warp after it has issued the stores of the tile ending at tile_end.
-	__device__ __forceinline__ void apply(uint_t<U>* __restrict__ target, uint64_t tile_end, shared_t&)
-	{
-		__syncwarp(); // orders the tile's stores before the patch stores
-		while (true) {
-			const bool mine = lane_index() >= spent && window_base + lane_index() < count && position < tile_end;
-			spent += __popc(__ballot_sync(full_mask, mine));
-			if (mine) { target[position] = value; }
-			if (spent < warp_size) { break; }
-			window_base += warp_size; spent = 0;
-			position = next_position; value = next_value;
-			load_next_window();
-			if (window_base >= count) { break; }
-		}
-	}
-};
-
-// Patches with run-compressed positions: the arguments of scatter::compressed_indices::scatter
-// (SURVEY.md Appendix A.11).  Positions are decoded a window at a time into the warp's slice of shared
-// memory -- 32 run descriptors (one per lane), a warp scan of the run lengths, then the patches, each lane
-// locating its patches' runs by binary search -- and consumed from there as the tiles advance.
-template <unsigned IndexSize, unsigned U, unsigned II, unsigned RL>
-struct compressed_index_patches {
-	struct shared_t {
-		uint_t<IndexSize> positions[window_patches];
-		uint64_t          run_baselines[warp_size];
-		uint64_t          run_offset_starts[warp_size];  // byte offset of the run's first offset
-		uint32_t          run_ends[warp_size];           // inclusive scan of the staged runs' (remaining, clamped) lengths
-		uint8_t           run_widths[warp_size];         // bytes per offset
-	};
-	const uint_t<U>*          __restrict__ data;
-	const uint_t<RL>*         __restrict__ run_lengths;
-	const unsigned char*      __restrict__ run_offset_sizes;
-	const uint_t<IndexSize>*  __restrict__ run_baselines;
-	const uint_t<II>*         __restrict__ run_offsets_start_positions;
-	const unsigned char*      __restrict__ offset_bytes;
-	const uint_t<II>*         __restrict__ anchors;
-	uint64_t                               anchoring_period;
-	uint64_t                               num_runs;
-	uint64_t                               count;          // number of patches
-
-	// the stream's state; uniform over the warp
-	uint64_t  cursor;        // the first patch not yet applied
-	uint64_t  window_first;  // shared.positions[j] is the position of patch window_first + j, for window_first + j < window_end
-	uint64_t  window_end;
-	uint64_t  next_run;      // the first run with patches at or past window_end ...
-	uint64_t  next_run_skip; // ... and how many of its patches are before window_end
-	bool      exhausted;
-	uint_t<U> my_value;      // data[cursor + lane] as of the last prefetch()
-
-	__device__ __forceinline__ uint64_t first_position_of_run(uint64_t run) const
-	{
-		const unsigned width = (unsigned) __ldg(run_offset_sizes + run) / 8;
-		const uint8_t* offsets = offset_bytes + (uint64_t) __ldg(run_offsets_start_positions + run) * IndexSize;
-		return (uint64_t)(uint_t<IndexSize>)((uint64_t) __ldg(run_baselines + run) + ci_detail::load_offset(offsets, 0, width));
-	}
-
-	// Decode the positions of the next (up to) window_patches patches.  Whole warp.
-	__device__ __forceinline__ void refill(shared_t& shared)
-	{
-		const unsigned lane = lane_index();
-		const unsigned runs_here = (unsigned) minimum<uint64_t>(warp_size, num_runs - next_run);
-		uint32_t length = 0;
-		__syncwarp(); // every lane is done with the previous window
-		if (lane < runs_here) {
-			const uint64_t run = next_run + lane;
-			uint64_t remaining = (uint64_t) __ldg(run_lengths + run);
-			if (lane == 0) { remaining = remaining > next_run_skip ? remaining - next_run_skip : 0; }
-			length = (uint32_t) minimum<uint64_t>(remaining, window_patches + 1);
-			shared.run_baselines[lane] = (uint64_t) __ldg(run_baselines + run);
-			shared.run_offset_starts[lane] = (uint64_t) __ldg(run_offsets_start_positions + run) * IndexSize;
-			shared.run_widths[lane] = (uint8_t)(__ldg(run_offset_sizes + run) / 8);
-		}
-		const uint32_t end = warp_inclusive_sum(length);
-		shared.run_ends[lane] = end;
-		__syncwarp();
-		const uint32_t staged_total = shuffle_from(end, warp_size - 1);
-		const uint32_t fill = (uint32_t) minimum<uint64_t>(minimum<uint32_t>(staged_total, window_patches), count - window_end);
-		for (uint32_t q = lane; q < fill; q += warp_size) {
-			unsigned lo = 0, hi = runs_here - 1; // the first staged run whose end exceeds q
-			while (lo < hi) {
-				const unsigned mid = (lo + hi) / 2;
-				if (shared.run_ends[mid] > q) { hi = mid; } else { lo = mid + 1; }
-			}
-			const uint32_t preceding = lo == 0 ? 0 : shared.run_ends[lo - 1];
-			const uint64_t j = (uint64_t)(q - preceding) + (lo == 0 ? next_run_skip : 0);
-			shared.positions[q] = (uint_t<IndexSize>)(shared.run_baselines[lo] +
-				ci_detail::load_offset(offset_bytes + shared.run_offset_starts[lo], j, shared.run_widths[lo]));
-		}
-		const unsigned finished_runs = __popc(__ballot_sync(full_mask, lane < runs_here && end <= fill));
-		if (finished_runs == 0) { next_run_skip += fill; }
-		else { next_run_skip = finished_runs < runs_here ? fill - shuffle_from(end, finished_runs - 1) : 0; }
-		next_run += finished_runs;
-		window_first = window_end;
-		window_end += fill;
-		exhausted = fill == 0;
-		__syncwarp(); // publishes shared.positions
-	}
-
-	// Apply (or, with Apply == false, skip) the patches with positions below `limit`.  Whole warp.
-	template <bool Apply>
-	__device__ __forceinline__ void consume(uint_t<U>* __restrict__ target, uint64_t limit, shared_t& shared, bool value_prefetched)
-	{
-		while (true) {
-			if (cursor == window_end) {
-				if (exhausted || window_end >= count) { break; }
-				refill(shared);
-				if (exhausted) { break; }
-			}
-			const uint64_t available = window_end - cursor;
-			bool mine = lane_index() < available;
-			uint_t<IndexSize> position = 0;
-			if (mine) {
-				position = shared.positions[cursor - window_first + lane_index()];
-				mine = position < limit;
-			}
-			const unsigned matched = __popc(__ballot_sync(full_mask, mine));
-			if (Apply && mine) { target[position] = value_prefetched ? my_value : __ldg(data + cursor + lane_index()); }
-			cursor += matched;
-			value_prefetched = false;
-			if (matched < warp_size && matched < available) { break; } // the next patch is at or beyond the limit
-		}
-	}
-
-	__device__ __forceinline__ void seek(uint64_t first_position, shared_t& shared)
-	{
-		cursor = window_first = window_end = next_run = next_run_skip = 0;
-		exhausted = count == 0 || num_runs == 0;
-		if (first_position == 0 || exhausted) { return; }
-		const uint64_t num_periods = (count + anchoring_period - 1) / anchoring_period;
-		const uint64_t period = warp_lower_bound(num_periods, first_position,
-			[&](uint64_t a) { return first_position_of_run((uint64_t) __ldg(anchors + a)); });
-		// the period before may hold patches at or beyond first_position in its later part; within it, so may
-		// the last run which begins below first_position, while the runs before that one are skipped whole
-		const uint64_t start = period == 0 ? 0 : period - 1;
-		const uint64_t first_run = (uint64_t) __ldg(anchors + start);
-		const uint64_t past_last_run = start + 1 < num_periods ? (uint64_t) __ldg(anchors + start + 1) : num_runs;
-		const uint64_t runs_below = warp_lower_bound(past_last_run - first_run, first_position,
-			[&](uint64_t i) { return first_position_of_run(first_run + i); });
-		const uint64_t whole_runs = runs_below == 0 ? 0 : runs_below - 1;
-		uint64_t skipped = 0;
-		for (uint64_t i = lane_index(); i < whole_runs; i += warp_size) { skipped += (uint64_t) __ldg(run_lengths + first_run + i); }
-		skipped = warp_sum(skipped);
-		next_run = first_run + whole_runs;
-		cursor = window_first = window_end = start * anchoring_period + skipped;
-		consume<false>(nullptr, first_position, shared, false);
-	}
-
-	// Request this lane's candidate value for the coming tile (an L1 hit most of the time: the cursor advances
-	// by a few patches per tile).
-	__device__ __forceinline__ void prefetch()
-	{
-		const uint64_t i = cursor + lane_index();
-		if (i < count) { my_value = __ldg(data + i); }
-	}
-
-	__device__ __forceinline__ void apply(uint_t<U>* __restrict__ target, uint64_t tile_end, shared_t& shared)
-	{
-		__syncwarp(); // orders the tile's stores before the patch stores
-		consume<true>(target, tile_end, shared, true);
-	}
-};
+constexpr unsigned unroll = GIDDY_PATCHED_UNROLL;
+constexpr unsigned max_warps_per_block = GIDDY_ELEMENTWISE_BLOCK_THREADS / 32; // the launchers refuse larger blocks
 
 // ---- decoders ----------------------------------------------------------------------------------------
 // load(v): the compressed bytes of output vector v; decode(pack, v): its 16 decoded bytes;
@@ -347,73 +128,131 @@ struct frame_of_reference_decoder {
 	}
 };
 
+// ---- the tile index -----------------------------------------------------------------------------------
+
+// ranges[t] = { first, past_last }: tile t's patches are [first, past_last) of the (ascending) patch list; tiles without
+// patches keep the zeroes the launcher filled the array with.  One thread per patch, no loops: patch j opens its tile's
+// range if its predecessor lies in an earlier tile and closes it if its successor lies in a later one.
+template <unsigned IndexSize>
+struct alignas(2 * sizeof(size_type<IndexSize>)) patch_range_t { size_type<IndexSize> first, past_last; };
+
+template <unsigned IndexSize>
+__global__ void patch_tile_ranges(
+	patch_range_t<IndexSize>*  __restrict__  ranges,
+	const uint_t<IndexSize>*   __restrict__  positions,
+	size_type<IndexSize>                     num_patches,
+	unsigned                                 log2_tile_elements,
+	uint64_t                                 num_tiles)
+{
+	for (uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; j < num_patches; j += (uint64_t) gridDim.x * blockDim.x) {
+		const uint64_t tile = (uint64_t) __ldg(positions + j) >> log2_tile_elements;
+		if (tile >= num_tiles) { continue; } // beyond the column: never applied
+		const bool opens = j == 0 || ((uint64_t) __ldg(positions + j - 1) >> log2_tile_elements) != tile;
+		const bool closes = j + 1 == num_patches || ((uint64_t) __ldg(positions + j + 1) >> log2_tile_elements) != tile;
+		if (opens) { ranges[tile].first = (size_type<IndexSize>) j; }
+		if (closes) { ranges[tile].past_last = (size_type<IndexSize>)(j + 1); }
+	}
+}
+
 // ---- the tile loop -------------------------------------------------------------------------------------
 
-template <unsigned U, typename Decoder, typename Patches>
-__device__ __forceinline__ void decode_and_patch(const Decoder& decoder, Patches& patches, typename Patches::shared_t& shared, uint64_t length)
+template <unsigned IndexSize, unsigned U, typename Decoder>
+__device__ __forceinline__ void decode_and_patch(
+	const Decoder&                                decoder,
+	const uint_t<U>*             __restrict__     patch_values,
+	const uint_t<IndexSize>*     __restrict__     patch_positions,
+	const patch_range_t<IndexSize>*  __restrict__ tile_ranges,
+	unsigned                                      log2_tile_elements,
+	uint64_t                                      length)
 {
 	constexpr unsigned E = Decoder::E;
 	uint_t<U>* __restrict__ const decompressed = decoder.decompressed;
 	const unsigned lane = lane_index();
-	const bool vectorizable = decoder.vectorizable();
-	const uint64_t elements_per_tile = (uint64_t) warp_size * unroll * (vectorizable ? E : 1);
-	const uint64_t num_tiles = (length + elements_per_tile - 1) / elements_per_tile;
-	const uint64_t first_tile = num_tiles * global_warp_index() / num_warps_in_grid();
-	const uint64_t past_last_tile = num_tiles * (global_warp_index() + 1) / num_warps_in_grid();
-	if (first_tile == past_last_tile) { return; }
+	const uint64_t elements_per_tile = (uint64_t) 1 << log2_tile_elements;
+	const bool vectorizable = elements_per_tile == (uint64_t) warp_size * unroll * E && decoder.vectorizable(); // (the launcher sized the tiles by the same test)
+	const uint64_t num_tiles = (length + elements_per_tile - 1) >> log2_tile_elements;
+	constexpr unsigned vectors_per_tile = warp_size * unroll;
+	__shared__ uint4 stage_of_warp[max_warps_per_block][vectors_per_tile]; // 4 KiB per warp
+	uint4* const stage_vectors = stage_of_warp[warp_index_in_block()];
 
-	patches.seek(first_tile * elements_per_tile, shared);
+	// (a warp takes tiles w, w + W, ...; each tile's patch range is requested an iteration ahead, so that the patches
+	// themselves can be requested together with the tile's compressed vectors: one memory round trip per tile, not two)
+	uint64_t tile = global_warp_index();
+	if (tile >= num_tiles) { return; }
+	patch_range_t<IndexSize> next_range = tile_ranges[tile];
+	#pragma unroll 1
+	for (; tile < num_tiles; tile += num_warps_in_grid()) {
+		const uint64_t tile_start = tile << log2_tile_elements;
+		const uint64_t tile_end = minimum(tile_start + elements_per_tile, length);
+		const patch_range_t<IndexSize> range = next_range;
+		if (tile + num_warps_in_grid() < num_tiles) { next_range = tile_ranges[tile + num_warps_in_grid()]; }
+		const uint64_t first_patch = range.first, past_last_patch = range.past_last;
+		const uint64_t num_patches = past_last_patch > first_patch ? past_last_patch - first_patch : 0; // uniform over the warp
 
-	if (!vectorizable) {
-		#pragma unroll 1
-		for (uint64_t tile = first_tile; tile < past_last_tile; tile++) {
-			const uint64_t tile_start = tile * elements_per_tile;
-			const uint64_t tile_end = minimum(tile_start + elements_per_tile, length);
-			patches.prefetch();
+		if (vectorizable) {
+			const uint64_t first_vector = tile * vectors_per_tile;
+			const unsigned num_vectors = (unsigned)(tile_end / E - first_vector); // all of them but for the column's last tile
+			byte_pack<Decoder::in_bytes> in[unroll];
+			#pragma unroll
+			for (unsigned k = 0; k < unroll; k++) {
+				const unsigned v = k * warp_size + lane;
+				if (v < num_vectors) { in[k] = decoder.load(first_vector + v); }
+			}
+			uint_t<IndexSize> position = 0;
+			uint_t<U> value = 0;
+			if (lane < num_patches) { position = __ldg(patch_positions + first_patch + lane); value = __ldg(patch_values + first_patch + lane); }
+			if (num_patches != 0 && num_vectors == vectors_per_tile) {
+				// A patch stored to global memory after the vector which contains it is a partial write of a 32-byte
+				// sector: it merges in L2 (no HBM traffic) but each one still costs L2 a read-modify-write.  So the tile
+				// is patched BEFORE it is stored: through the warp's slice of shared memory, where a patch is a plain
+				// element store, and out again as whole vectors.
+				#pragma unroll
+				for (unsigned k = 0; k < unroll; k++) {
+					const byte_pack<16> out = decoder.decode(in[k], first_vector + k * warp_size + lane);
+					stage_vectors[k * warp_size + lane] = make_uint4(out.u32[0], out.u32[1], out.u32[2], out.u32[3]);
+				}
+				__syncwarp();
+				uint_t<U>* const stage_elements = reinterpret_cast<uint_t<U>*>(stage_vectors);
+				if (lane < num_patches) { stage_elements[(uint64_t) position - tile_start] = value; }
+				for (uint64_t q = first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
+					stage_elements[(uint64_t) __ldg(patch_positions + q) - tile_start] = __ldg(patch_values + q);
+				}
+				__syncwarp();
+				#pragma unroll
+				for (unsigned k = 0; k < unroll; k++) { store_streaming_16(decompressed + (first_vector + k * warp_size + lane) * E, stage_vectors[k * warp_size + lane]); }
+				__syncwarp(); // the next tile's vectors go to the same slots
+			}
+			else {
+				#pragma unroll
+				for (unsigned k = 0; k < unroll; k++) {
+					const unsigned v = k * warp_size + lane;
+					if (v < num_vectors) { store_pack_16(decompressed + (first_vector + v) * E, decoder.decode(in[k], first_vector + v)); }
+				}
+				// the column's < E trailing elements (in its last tile only)
+				const uint64_t i = (first_vector + num_vectors) * E + lane;
+				if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
+				if (num_patches != 0) { // the column's last, partial tile: patches stored after their vectors
+					__syncwarp(); // orders the tile's stores before the patch stores
+					if (lane < num_patches) { decompressed[position] = value; }
+					for (uint64_t q = first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
+						decompressed[__ldg(patch_positions + q)] = __ldg(patch_values + q);
+					}
+				}
+			}
+		}
+		else {
 			#pragma unroll
 			for (unsigned k = 0; k < unroll; k++) {
 				const uint64_t i = tile_start + k * warp_size + lane;
 				if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
 			}
-			patches.apply(decompressed, tile_end, shared);
+			if (num_patches != 0) {
+				__syncwarp();
+				for (uint64_t q = first_patch + lane; q < past_last_patch; q += warp_size) {
+					decompressed[__ldg(patch_positions + q)] = __ldg(patch_values + q);
+				}
+			}
 		}
-		return;
-	}
-
-	constexpr unsigned vectors_per_tile = warp_size * unroll;
-	auto vectors_in_tile = [&](uint64_t tile) { // all of them but for the column's last tile
-		return (unsigned)(minimum((tile + 1) * elements_per_tile, length) / E - tile * vectors_per_tile);
-	};
-	byte_pack<Decoder::in_bytes> in[unroll], in_next[unroll];
-	auto request = [&](byte_pack<Decoder::in_bytes> (&packs)[unroll], uint64_t tile) {
-		const unsigned num_vectors = vectors_in_tile(tile);
-		#pragma unroll
-		for (unsigned k = 0; k < unroll; k++) {
-			const unsigned v = k * warp_size + lane;
-			if (v < num_vectors) { packs[k] = decoder.load(tile * vectors_per_tile + v); }
-		}
-	};
-	request(in_next, first_tile);
-
-	#pragma unroll 1
-	for (uint64_t tile = first_tile; tile < past_last_tile; tile++) {
-		const uint64_t tile_start = tile * elements_per_tile;
-		const uint64_t tile_end = minimum(tile_start + elements_per_tile, length);
-		const uint64_t first_vector = tile * vectors_per_tile;
-		const unsigned num_vectors = vectors_in_tile(tile);
-		#pragma unroll
-		for (unsigned k = 0; k < unroll; k++) { in[k] = in_next[k]; }
-		if (tile + 1 < past_last_tile) { request(in_next, tile + 1); }
-		patches.prefetch();
-		#pragma unroll
-		for (unsigned k = 0; k < unroll; k++) {
-			const unsigned v = k * warp_size + lane;
-			if (v < num_vectors) { store_pack_16(decompressed + (first_vector + v) * E, decoder.decode(in[k], first_vector + v)); }
-		}
-		// the column's < E trailing elements (in its last tile only)
-		const uint64_t i = (first_vector + num_vectors) * E + lane;
-		if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
-		patches.apply(decompressed, tile_end, shared);
 	}
 }
 
@@ -422,12 +261,12 @@ __device__ __forceinline__ void decode_and_patch(const Decoder& decoder, Patches
 // -------------------------------------------------------------------------------------------------
 // dictionary::decompress (reference src/kernels/decompression/dictionary.cuh:61-75) followed by
 // scatter::scatter (src/kernels/data_layout/scatter.cuh:26-46) with OutputIndexSize = InputIndexSize =
-// IndexSize, in one pass.  Parameters: the former's, then the latter's minus the target.
+// IndexSize, in one pass.  Parameters: the former's, then the latter's minus the target, then the tile index.
 //   decompressed[i] = dictionary_entries[compressed_input[i]];  decompressed[patch_indices[k]] = patch_data[k]
 // patch_indices must be ascending.
 // -------------------------------------------------------------------------------------------------
 template <unsigned IndexSize, unsigned U, unsigned DictionaryIndexSize>
-__global__ void patched_dictionary_decompress(
+__global__ void __launch_bounds__(GIDDY_ELEMENTWISE_BLOCK_THREADS, GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR) patched_dictionary_decompress(
 	uint_t<U>*                          __restrict__  decompressed,
 	const uint_t<DictionaryIndexSize>*  __restrict__  compressed_input,
 	const uint_t<U>*                    __restrict__  dictionary_entries,
@@ -436,59 +275,38 @@ __global__ void patched_dictionary_decompress(
 	bool                                              cache_dictionary_in_shared_memory,
 	const uint_t<U>*                    __restrict__  patch_data,
 	const uint_t<IndexSize>*            __restrict__  patch_indices,
-	size_type<IndexSize>                              num_patches)
+	const patched_detail::patch_range_t<IndexSize>*  __restrict__  tile_ranges,
+	unsigned                                          log2_tile_elements)
 {
-	using patches_t = patched_detail::index_list_patches<IndexSize, U>;
-	__shared__ typename patches_t::shared_t shared[patched_detail::max_warps_per_block];
 	patched_detail::dictionary_decoder<IndexSize, U, DictionaryIndexSize> decoder;
 	decoder.decompressed = decompressed;
 	decoder.compressed_input = compressed_input;
 	decoder.setup(dictionary_entries, num_dictionary_entries, cache_dictionary_in_shared_memory);
-	patches_t patches;
-	patches.data = patch_data; patches.indices = patch_indices; patches.count = num_patches;
-	patched_detail::decode_and_patch<U>(decoder, patches, shared[warp_index_in_block()], length);
+	patched_detail::decode_and_patch<IndexSize, U>(decoder, patch_data, patch_indices, tile_ranges, log2_tile_elements, length);
 }
 
 // -------------------------------------------------------------------------------------------------
 // frame_of_reference::decompress (reference src/kernels/decompression/frame_of_reference.cuh:35-80)
 // followed by scatter::compressed_indices::scatter (src/kernels/data_layout/compressed_indices_scatter.cuh:
-// 219-271) with OutputIndexSize = IndexSize and RunLengthSize = InputIndexSize, in one pass.  Parameters: the
-// former's, then the latter's minus the target.  Patch positions must be ascending over the whole patch list.
+// 219-271) with OutputIndexSize = IndexSize and RunLengthSize = InputIndexSize, in one pass.  The latter's
+// positions arrive decoded (expand_compressed_indices, kernels/scatter.cuh) and must be ascending over the whole
+// patch list.
 // -------------------------------------------------------------------------------------------------
-template <unsigned IndexSize, unsigned U, unsigned C, int Model, unsigned ModelIndexSize, unsigned InputIndexSize>
-__global__ void patched_frame_of_reference_decompress(
-	uint_t<U>*                     __restrict__  decompressed,
-	const int_t<C>*                __restrict__  compressed_input,
-	const int32_t*                 __restrict__  segment_model_coefficients,
-	size_type<IndexSize>                         length,
-	size_type<IndexSize>                         segment_length,
-	const uint_t<U>*               __restrict__  data_to_scatter,
-	const uint_t<InputIndexSize>*  __restrict__  scatter_position_run_lengths,
-	const unsigned char*           __restrict__  scatter_position_run_individual_offset_sizes,
-	const uint_t<IndexSize>*       __restrict__  scatter_position_run_baseline_values,
-	const uint_t<InputIndexSize>*  __restrict__  scatter_position_run_offsets_start_positions,
-	const unsigned char*           __restrict__  scatter_position_offset_bytes,
-	const uint_t<InputIndexSize>*  __restrict__  scatter_position_anchors,
-	uint_t<InputIndexSize>                       anchoring_period,
-	uint_t<InputIndexSize>                       num_scatter_position_runs,
-	size_type<InputIndexSize>                    data_length)
+template <unsigned IndexSize, unsigned U, unsigned C, int Model, unsigned ModelIndexSize>
+__global__ void __launch_bounds__(GIDDY_ELEMENTWISE_BLOCK_THREADS, GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR) patched_frame_of_reference_decompress(
+	uint_t<U>*                   __restrict__  decompressed,
+	const int_t<C>*              __restrict__  compressed_input,
+	const int32_t*               __restrict__  segment_model_coefficients,
+	size_type<IndexSize>                       length,
+	size_type<IndexSize>                       segment_length,
+	const uint_t<U>*             __restrict__  data_to_scatter,
+	const uint_t<IndexSize>*     __restrict__  scatter_positions,
+	const patched_detail::patch_range_t<IndexSize>*  __restrict__  tile_ranges,
+	unsigned                                   log2_tile_elements)
 {
-	using patches_t = patched_detail::compressed_index_patches<IndexSize, U, InputIndexSize, InputIndexSize>;
-	__shared__ typename patches_t::shared_t shared[patched_detail::max_warps_per_block];
 	const patched_detail::frame_of_reference_decoder<IndexSize, U, C, Model, ModelIndexSize> decoder(
 		decompressed, compressed_input, segment_model_coefficients, segment_length);
-	patches_t patches;
-	patches.data = data_to_scatter;
-	patches.run_lengths = scatter_position_run_lengths;
-	patches.run_offset_sizes = scatter_position_run_individual_offset_sizes;
-	patches.run_baselines = scatter_position_run_baseline_values;
-	patches.run_offsets_start_positions = scatter_position_run_offsets_start_positions;
-	patches.offset_bytes = scatter_position_offset_bytes;
-	patches.anchors = scatter_position_anchors;
-	patches.anchoring_period = anchoring_period;
-	patches.num_runs = num_scatter_position_runs;
-	patches.count = data_length;
-	patched_detail::decode_and_patch<U>(decoder, patches, shared[warp_index_in_block()], length);
+	patched_detail::decode_and_patch<IndexSize, U>(decoder, data_to_scatter, scatter_positions, tile_ranges, log2_tile_elements, length);
 }
 
 } // namespace kernels
