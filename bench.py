@@ -206,6 +206,8 @@ def host_sample(np, log2_elements, segment_length, seed):
 def time_host_decoder(np, sample, segment_length, passes, seconds=None):
     """Decode the sample `passes` times -- or, with `seconds`, as many times as fit (at least 3, at most 400)."""
     from oracle import giddy_oracle as O  # the checker / CPU baseline: the only use of oracle/ in this file
+    # all the host threads this process may use -- torchrun exports OMP_NUM_THREADS=1, which would leave the decoder on one core
+    O.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     out = np.empty(sample["n"], dtype=np.uint32)
     out[:] = 0  # first touch
     times = []
@@ -285,6 +287,7 @@ def run_product_arm(args):
     if distributed:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line and nothing else
         dist.init_process_group("nccl", device_id=device)
 
     library = g.default_library()

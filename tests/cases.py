@@ -47,8 +47,22 @@ def random_uint(r, size, n, bits=None):
     return r.integers(0, 1 << bits, n, dtype=np.uint64).astype(UINT[size])
 
 
-def run_case_on_gpu(case, library=None, limits=None):
-    """Copy the case's inputs to the current CUDA device, decode, and return the output as numpy."""
+MISALIGNMENT = 65  # elements: a buffer starting this far into an allocation is element-aligned but never 16-byte aligned
+
+
+def _misaligned(tensor):
+    """A copy of the tensor which starts MISALIGNMENT elements into its allocation."""
+    import torch
+    holder = torch.zeros(tensor.numel() + MISALIGNMENT, dtype=tensor.dtype, device=tensor.device)
+    view = holder[MISALIGNMENT:]
+    view.copy_(tensor.reshape(-1))
+    return view.reshape(tensor.shape)
+
+
+def run_case_on_gpu(case, library=None, limits=None, misaligned=False):
+    """Copy the case's inputs to the current CUDA device, decode, and return the output as numpy.
+    misaligned: every buffer starts at an address which is a multiple of its element size only (the kernels'
+    vector paths want 16-byte alignment; without it their element-wise paths must produce the same output)."""
     import torch
     device = torch.device("cuda")
     tensors = {k: torch.from_numpy(_as_torch_compatible(v)).to(device) for k, v in case.inputs.items()}
@@ -58,6 +72,12 @@ def run_case_on_gpu(case, library=None, limits=None):
     else:
         # poison the output (plus a guard zone) so that unwritten or over-written elements show up
         out = torch.full(((case.output_elements + 64) * itemsize,), 0x5A, dtype=torch.uint8, device=device).view(_torch_int(itemsize))
+    if misaligned:
+        # (the compressed-indices offset bytes hold 16/32/64-bit items at offsets aligned relative to the array's start: the
+        # format itself wants that array aligned, in the reference as here)
+        tensors = {k: (v if k == "scatter_position_offset_bytes" else _misaligned(v)) for k, v in tensors.items()}
+        out = _misaligned(out)
+        assert out.data_ptr() % 16 != 0
     case.launch(out, tensors, library, limits)
     torch.cuda.synchronize()
     result = out.cpu().numpy().view(case.expected.dtype)

@@ -36,6 +36,17 @@ def test_matches_oracle_under_block_size_limits(case, limits, library):
     assert (got == case.expected).all(), _mismatch_report(case, got)
 
 
+# Alignment is a preference of the kernels, never a requirement: with every buffer starting at a
+# merely element-aligned address the element-wise paths run, and must decode to the same column.
+MISALIGNED = [c for c in ALL_CASES if c.output_elements <= 300000][::2]
+
+
+@pytest.mark.parametrize("case", MISALIGNED, ids=lambda c: c.name)
+def test_matches_oracle_with_misaligned_buffers(case, library):
+    got = cases.run_case_on_gpu(case, library, misaligned=True)
+    assert (got == case.expected).all(), _mismatch_report(case, got)
+
+
 @pytest.mark.parametrize("case", [c for c in ALL_CASES if c.ref_ok], ids=lambda c: c.name)
 def test_matches_reference_kernels(case, library, reference_library):
     """Drop-in check: same inputs, same named arguments, through the same C ABI, into the reference's

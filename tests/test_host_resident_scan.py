@@ -121,3 +121,41 @@ def test_host_resident_example_reproduces_the_known_answer(library):
     result = subprocess.run([binary], capture_output=True, text=True)
     assert result.returncode == 0, result.stdout + result.stderr
     assert result.stdout.count("SUCCESS") == 3, result.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True], ids=["enqueued", "graph"])
+def test_scan_with_kernels_which_take_a_workspace(library, graph):
+    """The long-segment Delta path (cooperative launch, look-back workspace) and a patched decoder (tile index workspace)
+    inside a scan: both allocate stream-ordered scratch memory from the library's pool, which must also work while the
+    scan is being captured into a CUDA graph."""
+    import torch
+    device = torch.device("cuda")
+    delta = cases.delta_case(21, 3 << 16, 1 << 16, 8, 4)              # 3 long segments: the look-back kernel
+    patched = cases.patched_dictionary_case(22, 1 << 17, 8, 1, 256, 1300)
+    scan = library.create_scan(2)
+    outs, expected = [], []
+    for index, case in enumerate((delta, patched)):
+        host = {k: torch.from_numpy(cases._as_torch_compatible(v)).pin_memory() for k, v in case.inputs.items()}
+        dev = {k: torch.zeros_like(v, device=device) for k, v in host.items()}
+        out = torch.zeros(case.output_elements + 64, dtype=cases._torch_int(case.expected.dtype.itemsize), device=device)
+        chunk = scan.chunk(index)
+        for k in host:
+            chunk.copy(dev[k], host[k])
+        outs.append((out, dev, host))
+        expected.append(case.expected)
+    # record the launches through the scheme helpers (stream = the chunk)
+    out, dev, _ = outs[0]
+    S.delta(out, dev["compressed_input"], dev["anchor_values"], 3 << 16, 1 << 16, uncompressed_size=8,
+            compressed_size=4, stream=scan.chunk(0), library=library)
+    out, dev, _ = outs[1]
+    S.patched_dictionary(out, dev["compressed_input"], dev["dictionary_entries"], 1 << 17, 256, dev["patch_data"], dev["patch_indices"],
+                         1300, uncompressed_size=8, dictionary_index_size=1, stream=scan.chunk(1), library=library)
+    scan.set_graph_replay(graph)
+    for _ in range(2):
+        for out, dev, _host in outs:
+            out.zero_()
+        scan.run()
+        torch.cuda.synchronize()
+        for (out, _dev, _host), want in zip(outs, expected):
+            assert (out[:len(want)].cpu().numpy().view(want.dtype) == want).all()
