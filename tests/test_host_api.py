@@ -175,3 +175,28 @@ def test_key_set_equals_the_rebuilt_reference_factory(library, reference_library
     documented extensions under decompression::composite::)."""
     ours = [k for k in library.registered_keys() if not k.startswith("decompression::composite::")]
     assert sorted(reference_library.registered_keys()) == sorted(ours)
+
+
+def test_policies_of_the_persistent_kernels(library):
+    """Large dictionaries, long Delta segments and the patched decoders run persistent grids sized from the device."""
+    sms = PROPS.multiprocessor_count
+    # a 240 KB dictionary and a column 1000x its size: one 1024-thread CTA per multiprocessor holding as much as fits
+    c = resolve(library, S.dictionary_key(4, 4, 2), {"num_dictionary_entries": g.size_t(60000), "data_length": g.size_t(1 << 27)})
+    assert (c.grid, c.block) == (sms, 1024) and 200 * 1024 < c.dynamic_shared_memory_size <= 227 * 1024 and c.dynamic_shared_memory_size % 16 == 0
+    # the same dictionary for a short column: gathered through L1/L2
+    c = resolve(library, S.dictionary_key(4, 4, 2), {"num_dictionary_entries": g.size_t(60000), "data_length": g.size_t(1 << 22)})
+    assert c.block == 256 and c.dynamic_shared_memory_size == 0
+    # 160 KB: all of it in shared memory
+    c = resolve(library, S.dictionary_key(4, 4, 2), {"num_dictionary_entries": g.size_t(40000), "data_length": g.size_t(1 << 27)})
+    assert (c.grid, c.block, c.dynamic_shared_memory_size) == (sms, 1024, 160000)
+    # Delta over one long segment: tiles + decoupled look-back, 3 CTAs of 256 threads per multiprocessor
+    c = resolve(library, S.delta_key(4, 8, 4), {"length": g.size_t(1 << 26), "segment_length": g.size_t(1 << 26)})
+    assert (c.grid, c.block, c.dynamic_shared_memory_size) == (3 * sms, 256, 0)
+    # ... but anchored segments stay with a warp per segment
+    c = resolve(library, S.delta_key(4, 8, 4), {"length": g.size_t(1 << 26), "segment_length": g.size_t(4096)})
+    assert (c.grid, c.block) == ((1 << 14) // 8, 256)
+    # patched decoders: 5 CTAs of 256 threads per multiprocessor, warps striding over the tiles
+    c = resolve(library, S.patched_dictionary_key(4, 8, 1), {"num_dictionary_entries": g.size_t(256), "data_length": g.size_t(1 << 29)})
+    assert (c.grid, c.block, c.dynamic_shared_memory_size) == (5 * sms, 256, 2048)
+    c = resolve(library, S.patched_dictionary_key(4, 8, 1), {"num_dictionary_entries": g.size_t(256), "data_length": g.size_t(5000)})
+    assert c.grid == 2 and c.block == 256  # 5000 elements: two CTA tiles of 256 x 8 vectors x 2 elements
