@@ -26,8 +26,8 @@ ABI_SRCS  := $(wildcard $(SRC_DIR)/abi/*.cu)
 HOST_SRCS := $(wildcard $(SRC_DIR)/host/*.cpp)
 ABI_OBJS  := $(patsubst $(SRC_DIR)/abi/%.cu,$(BUILD_DIR)/abi/%.o,$(ABI_SRCS))
 HOST_OBJS := $(patsubst $(SRC_DIR)/host/%.cpp,$(BUILD_DIR)/host/%.o,$(HOST_SRCS))
-KERNEL_HDRS := $(wildcard $(SRC_DIR)/kernels/*.cuh) $(wildcard $(SRC_DIR)/abi/*.hpp) include/giddy_b200.h
-HOST_HDRS := $(wildcard include/giddy/*.hpp) $(wildcard include/giddy/*/*.hpp) $(wildcard include/giddy/*/*.h) include/giddy_b200.h
+KERNEL_HDRS := $(wildcard $(SRC_DIR)/kernels/*.cuh) $(wildcard $(SRC_DIR)/abi/*.hpp) include/giddy_b200.h $(wildcard include/giddy/*.h)
+HOST_HDRS := $(wildcard include/giddy/*.hpp) $(wildcard include/giddy/*.h) $(wildcard include/giddy/*/*.hpp) $(wildcard include/giddy/*/*.h) include/giddy_b200.h
 
 ORACLE_LIB := oracle/libgiddy_oracle.so
 

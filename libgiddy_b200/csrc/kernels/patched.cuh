@@ -163,34 +163,38 @@ __device__ __forceinline__ void decode_and_patch(
 	const uint_t<IndexSize>*     __restrict__     patch_positions,
 	const patch_range_t<IndexSize>*  __restrict__ tile_ranges,
 	unsigned                                      log2_tile_elements,
-	uint64_t                                      length)
+	size_type<IndexSize>                          length)
 {
+	// (element, vector and tile numbers are kept in the column's own index width: 32-bit arithmetic -- and half the
+	// registers -- for columns of up to 2^32 elements)
+	using index_t = size_type<IndexSize>;
 	constexpr unsigned E = Decoder::E;
 	uint_t<U>* __restrict__ const decompressed = decoder.decompressed;
 	const unsigned lane = lane_index();
-	const uint64_t elements_per_tile = (uint64_t) 1 << log2_tile_elements;
-	const bool vectorizable = elements_per_tile == (uint64_t) warp_size * unroll * E && decoder.vectorizable(); // (the launcher sized the tiles by the same test)
-	const uint64_t num_tiles = (length + elements_per_tile - 1) >> log2_tile_elements;
+	const index_t elements_per_tile = (index_t) 1 << log2_tile_elements;
+	const bool vectorizable = elements_per_tile == (index_t)(warp_size * unroll * E) && decoder.vectorizable(); // (the launcher sized the tiles by the same test)
+	const index_t num_tiles = (index_t)(((uint64_t) length + elements_per_tile - 1) >> log2_tile_elements);
 	constexpr unsigned vectors_per_tile = warp_size * unroll;
 	__shared__ uint4 stage_of_warp[max_warps_per_block][vectors_per_tile]; // 4 KiB per warp
 	uint4* const stage_vectors = stage_of_warp[warp_index_in_block()];
 
 	// (a warp takes tiles w, w + W, ...; each tile's patch range is requested an iteration ahead, so that the patches
 	// themselves can be requested together with the tile's compressed vectors: one memory round trip per tile, not two)
-	uint64_t tile = global_warp_index();
-	if (tile >= num_tiles) { return; }
-	patch_range_t<IndexSize> next_range = tile_ranges[tile];
+	const uint64_t first_tile = global_warp_index(), tile_stride = num_warps_in_grid();
+	if (first_tile >= num_tiles) { return; }
+	patch_range_t<IndexSize> next_range = tile_ranges[first_tile];
 	#pragma unroll 1
-	for (; tile < num_tiles; tile += num_warps_in_grid()) {
-		const uint64_t tile_start = tile << log2_tile_elements;
-		const uint64_t tile_end = minimum(tile_start + elements_per_tile, length);
+	for (index_t tile = (index_t) first_tile; ; ) {
+		const index_t tile_start = tile << log2_tile_elements;
+		const index_t tile_end = (index_t) minimum<uint64_t>((uint64_t) tile_start + elements_per_tile, length);
 		const patch_range_t<IndexSize> range = next_range;
-		if (tile + num_warps_in_grid() < num_tiles) { next_range = tile_ranges[tile + num_warps_in_grid()]; }
-		const uint64_t first_patch = range.first, past_last_patch = range.past_last;
-		const uint64_t num_patches = past_last_patch > first_patch ? past_last_patch - first_patch : 0; // uniform over the warp
+		const bool last_iteration = (uint64_t) tile + tile_stride >= num_tiles;
+		if (!last_iteration) { next_range = tile_ranges[tile + (index_t) tile_stride]; }
+		const index_t first_patch = range.first, past_last_patch = range.past_last;
+		const index_t num_patches = past_last_patch > first_patch ? past_last_patch - first_patch : 0; // uniform over the warp
 
 		if (vectorizable) {
-			const uint64_t first_vector = tile * vectors_per_tile;
+			const index_t first_vector = tile * vectors_per_tile;
 			const unsigned num_vectors = (unsigned)(tile_end / E - first_vector); // all of them but for the column's last tile
 			byte_pack<Decoder::in_bytes> in[unroll];
 			#pragma unroll
@@ -213,28 +217,30 @@ __device__ __forceinline__ void decode_and_patch(
 				}
 				__syncwarp();
 				uint_t<U>* const stage_elements = reinterpret_cast<uint_t<U>*>(stage_vectors);
-				if (lane < num_patches) { stage_elements[(uint64_t) position - tile_start] = value; }
-				for (uint64_t q = first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
-					stage_elements[(uint64_t) __ldg(patch_positions + q) - tile_start] = __ldg(patch_values + q);
+				// (a position outside the tile can only come from a list which is not ascending: ignored, not written wild)
+				if (lane < num_patches && (index_t)(position - tile_start) < elements_per_tile) { stage_elements[(index_t)(position - tile_start)] = value; }
+				for (uint64_t q = (uint64_t) first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
+					const index_t in_tile = (index_t)(__ldg(patch_positions + q) - tile_start);
+					if (in_tile < elements_per_tile) { stage_elements[in_tile] = __ldg(patch_values + q); }
 				}
 				__syncwarp();
 				#pragma unroll
-				for (unsigned k = 0; k < unroll; k++) { store_streaming_16(decompressed + (first_vector + k * warp_size + lane) * E, stage_vectors[k * warp_size + lane]); }
+				for (unsigned k = 0; k < unroll; k++) { store_streaming_16(decompressed + (uint64_t)(first_vector + k * warp_size + lane) * E, stage_vectors[k * warp_size + lane]); }
 				__syncwarp(); // the next tile's vectors go to the same slots
 			}
 			else {
 				#pragma unroll
 				for (unsigned k = 0; k < unroll; k++) {
 					const unsigned v = k * warp_size + lane;
-					if (v < num_vectors) { store_pack_16(decompressed + (first_vector + v) * E, decoder.decode(in[k], first_vector + v)); }
+					if (v < num_vectors) { store_pack_16(decompressed + (uint64_t)(first_vector + v) * E, decoder.decode(in[k], first_vector + v)); }
 				}
 				// the column's < E trailing elements (in its last tile only)
-				const uint64_t i = (first_vector + num_vectors) * E + lane;
+				const uint64_t i = (uint64_t)(first_vector + num_vectors) * E + lane;
 				if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
 				if (num_patches != 0) { // the column's last, partial tile: patches stored after their vectors
 					__syncwarp(); // orders the tile's stores before the patch stores
 					if (lane < num_patches) { decompressed[position] = value; }
-					for (uint64_t q = first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
+					for (uint64_t q = (uint64_t) first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
 						decompressed[__ldg(patch_positions + q)] = __ldg(patch_values + q);
 					}
 				}
@@ -243,16 +249,18 @@ __device__ __forceinline__ void decode_and_patch(
 		else {
 			#pragma unroll
 			for (unsigned k = 0; k < unroll; k++) {
-				const uint64_t i = tile_start + k * warp_size + lane;
+				const uint64_t i = (uint64_t) tile_start + k * warp_size + lane;
 				if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
 			}
 			if (num_patches != 0) {
 				__syncwarp();
-				for (uint64_t q = first_patch + lane; q < past_last_patch; q += warp_size) {
+				for (uint64_t q = (uint64_t) first_patch + lane; q < past_last_patch; q += warp_size) {
 					decompressed[__ldg(patch_positions + q)] = __ldg(patch_values + q);
 				}
 			}
 		}
+		if (last_iteration) { break; }
+		tile += (index_t) tile_stride;
 	}
 }
 
