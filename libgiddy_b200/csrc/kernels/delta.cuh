@@ -160,25 +160,6 @@ __device__ __forceinline__ void publish(tile_descriptor_t* d, uint32_t status, u
 	}
 }
 
-// the status and value held by a descriptor's two words
-template <unsigned U>
-__device__ __forceinline__ uint32_t parse(unsigned long long w0, unsigned long long w1, uint_t<U>& value)
-{
-	if (U <= 4) { value = (uint_t<U>) w0; return (uint32_t)(w0 >> 32); }
-	value = (uint_t<U>)((w0 & 0xffffffffull) | (w1 << 32));
-	const uint32_t s0 = (uint32_t)(w0 >> 32), s1 = (uint32_t)(w1 >> 32);
-	return s0 == s1 ? s0 : (uint32_t) tile_unknown;
-}
-
-// An asynchronous copy of a descriptor into shared memory (read in L2, no register held meanwhile); completed by
-// wait_for_descriptor_copies().
-__device__ __forceinline__ void copy_descriptor_async(tile_descriptor_t* shared_destination, const tile_descriptor_t* source)
-{
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(shared_address(shared_destination)), "l"(source) : "memory");
-}
-__device__ __forceinline__ void commit_descriptor_copies() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void wait_for_descriptor_copies() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 // the descriptor's status, and its value if the status is not tile_unknown
 template <unsigned U>
 __device__ __forceinline__ uint32_t peek(const tile_descriptor_t* d, uint_t<U>& value)
@@ -214,11 +195,8 @@ __device__ __forceinline__ T warp_sum(T x)
 // ends as soon as the descriptors up to the nearest one with an inclusive prefix have been seen (farther ones are
 // never waited for), or when all of them hold just aggregates.
 template <unsigned U>
-__device__ __forceinline__ uint_t<U> look_back(const tile_descriptor_t* descriptors, uint64_t tile, uint64_t tile_in_segment,
-	const tile_descriptor_t* first_poll = nullptr)
+__device__ __forceinline__ uint_t<U> look_back(const tile_descriptor_t* descriptors, uint64_t tile, uint64_t tile_in_segment)
 {
-	// first_poll: copies, taken a little earlier (asynchronously, into shared memory), of the first round's descriptors --
-	// entry q * 32 + lane is predecessor number q * 32 + lane; what they do not settle is polled in global memory as usual
 	unsigned polls = 0, rounds = 0; (void) polls; (void) rounds;
 	const unsigned lane = lane_index();
 	constexpr unsigned round_tiles = look_back_window * warp_size;
@@ -232,23 +210,17 @@ __device__ __forceinline__ uint_t<U> look_back(const tile_descriptor_t* descript
 		for (unsigned q = 0; q < look_back_window; q++) {
 			valid[q] = looked + q * warp_size + lane < tile_in_segment; // distance 0 = the immediate predecessor
 			status[q] = tile_unknown; value[q] = 0;
-			if (first_poll != nullptr && valid[q]) { status[q] = parse<U>(first_poll[q * warp_size + lane].word[0], first_poll[q * warp_size + lane].word[1], value[q]); }
 		}
-		bool have_first_poll = first_poll != nullptr;
-		first_poll = nullptr; // (later rounds start from nothing)
 		unsigned nearest; // distance (within this round) of the nearest tile with an inclusive prefix; round_tiles: none
 		rounds++;
 		while (true) {
-			if (!have_first_poll) {
-				polls++;
-				#pragma unroll
-				for (unsigned q = 0; q < look_back_window; q++) {
-					if (valid[q] && status[q] == tile_unknown) {
-						status[q] = peek<U>(descriptors + (tile - 1 - (looked + q * warp_size + lane)), value[q]);
-					}
+			polls++;
+			#pragma unroll
+			for (unsigned q = 0; q < look_back_window; q++) {
+				if (valid[q] && status[q] == tile_unknown) {
+					status[q] = peek<U>(descriptors + (tile - 1 - (looked + q * warp_size + lane)), value[q]);
 				}
 			}
-			have_first_poll = false;
 			nearest = round_tiles;
 			bool all_seen = true;
 			#pragma unroll
@@ -365,9 +337,9 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 		}
 		return preceding_warps;
 	};
-	auto scan_and_store_rows = [&](const byte_pack<E * C> (&deltas)[look_back_rows], const geometry_t& g, uint_t<U>& carry, unsigned first_row, unsigned past_last_row) {
+	auto scan_and_store = [&](const byte_pack<E * C> (&deltas)[look_back_rows], const geometry_t& g, uint_t<U> carry) {
 		#pragma unroll
-		for (unsigned r = first_row; r < past_last_row; r++) {
+		for (unsigned r = 0; r < look_back_rows; r++) {
 			const uint64_t p = warp_offset + r * row_elements;
 			uint_t<U> local[E];
 			uint_t<U> sum = 0;
@@ -392,25 +364,14 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 		}
 	};
 
-	auto scan_and_store = [&](const byte_pack<E * C> (&deltas)[look_back_rows], const geometry_t& g, uint_t<U> carry) {
-		scan_and_store_rows(deltas, g, carry, 0, look_back_rows);
-	};
-
 	if (Static) {
 		// Software pipeline, one barrier per tile.  While warp 0 looks back for tile k, the other warps wait for tile
 		// k+1's deltas (requested at the top of the iteration) and reduce them; after the barrier tile k+1's aggregate
 		// is published -- a whole scan-and-store phase before its own look-back begins, so that by then the
 		// neighbouring CTAs' aggregates are normally there and look-backs rarely have to poll twice -- and only
 		// then tile k is scanned and stored.
-		// The look-back's first poll is split off and hidden too: a third of the way into tile k's scan-and-store, warp 0
-		// starts asynchronous copies (cp.async, no registers held) of the descriptors of tile k+1's nearest predecessors
-		// into shared memory; by the time it looks back for tile k+1 they have landed, and only what they do not settle
-		// costs a round trip in the open.
 		__shared__ uint_t<U> totals[3][32];   // [tile ordinal % 3]: written an iteration ahead, read in two iterations
 		__shared__ uint_t<U> exclusives[2];
-		__shared__ tile_descriptor_t first_poll[look_back_window * warp_size];
-		constexpr unsigned rows_before_first_poll = look_back_rows / 3;
-		bool have_first_poll = false; // warp 0: copies for the current tile are under way
 		auto publish_totals = [&](const byte_pack<E * C> (&deltas)[look_back_rows], unsigned slot) {
 			uint_t<U> lane_total = 0;
 			#pragma unroll
@@ -449,9 +410,7 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 				uint_t<U> exclusive;
 				if (g.tile_in_segment == 0) { exclusive = __ldg(anchor_values + g.segment); }
 				else {
-					if (have_first_poll) { wait_for_descriptor_copies(); __syncwarp(); }
-					exclusive = look_back<U>(descriptors, tile, g.tile_in_segment, have_first_poll ? first_poll : nullptr);
-					__syncwarp(); // (the copies are read before the next ones are started)
+					exclusive = look_back<U>(descriptors, tile, g.tile_in_segment);
 					if (lane == 0) {
 						uint_t<U> aggregate = 0;
 						for (unsigned w = 0; w < num_warps; w++) { aggregate = (uint_t<U>)(aggregate + totals[slot][w]); }
@@ -469,19 +428,7 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 			GIDDY_DELTA_TRACE_POINT(tile, 4);
 			uint_t<U> carry = exclusives[parity];
 			for (unsigned w = 0; w < warp; w++) { carry = (uint_t<U>)(carry + totals[slot][w]); }
-			scan_and_store_rows(deltas, g, carry, 0, rows_before_first_poll);
-			if (warp == 0) {
-				have_first_poll = has_next && next_g.tile_in_segment != 0;
-				if (have_first_poll) {
-					#pragma unroll
-					for (unsigned q = 0; q < look_back_window; q++) {
-						const uint64_t distance = q * warp_size + lane;
-						if (distance < next_g.tile_in_segment) { copy_descriptor_async(&first_poll[q * warp_size + lane], descriptors + (next_tile - 1 - distance)); }
-					}
-					commit_descriptor_copies();
-				}
-			}
-			scan_and_store_rows(deltas, g, carry, rows_before_first_poll, look_back_rows);
+			scan_and_store(deltas, g, carry);
 			GIDDY_DELTA_TRACE_POINT(tile, 5);
 			if (!has_next) { return; }
 			#pragma unroll
