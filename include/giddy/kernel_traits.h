@@ -43,10 +43,10 @@
 #define GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS 256
 #endif
 #ifndef GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR
-#define GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR 3
+#define GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR 2
 #endif
 #ifndef GIDDY_DELTA_LOOK_BACK_ROWS
-#define GIDDY_DELTA_LOOK_BACK_ROWS 12
+#define GIDDY_DELTA_LOOK_BACK_ROWS 16
 #endif
 #ifndef GIDDY_DELTA_LOOK_BACK_WINDOW
 #define GIDDY_DELTA_LOOK_BACK_WINDOW 4             /* descriptors inspected per lane per look-back round */

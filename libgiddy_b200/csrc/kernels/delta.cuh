@@ -254,7 +254,7 @@ __device__ __forceinline__ uint_t<U> look_back(const tile_descriptor_t* descript
 //                   done whatever the grid -- the fall-back where a cooperative launch is not to be had.  (Drawing
 //                   tickets ahead of time is not an option: a drawn but unstarted tile stalls all its successors,
 //                   and the stalls chain up -- measured 20x slower.)
-template <unsigned U, unsigned C, unsigned E, bool Static>
+template <unsigned U, unsigned C, unsigned E, unsigned Rows, bool Static>
 __device__ __forceinline__ void decode_tiles_with_look_back(
 	uint_t<U>*        __restrict__  decompressed,
 	const uint_t<C>*  __restrict__  compressed_input,
@@ -270,14 +270,14 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 
 	const unsigned lane = lane_index(), warp = warp_index_in_block(), num_warps = warps_per_block();
 	constexpr unsigned row_elements = warp_size * E;
-	const uint64_t tile_elements = (uint64_t) num_warps * look_back_rows * row_elements;
+	const uint64_t tile_elements = (uint64_t) num_warps * Rows * row_elements;
 	const uint64_t tiles_per_segment = (segment_length + tile_elements - 1) / tile_elements;
 	const uint64_t num_segments = (length + segment_length - 1) / segment_length;
 	const uint64_t last_segment_length = length - (num_segments - 1) * segment_length;
 	const uint64_t num_tiles = (num_segments - 1) * tiles_per_segment + (last_segment_length + tile_elements - 1) / tile_elements;
 	unsigned long long* const ticket_counter = static_cast<unsigned long long*>(workspace);
 	tile_descriptor_t* const descriptors = reinterpret_cast<tile_descriptor_t*>(static_cast<unsigned char*>(workspace) + 32);
-	const uint64_t warp_offset = (uint64_t) warp * look_back_rows * row_elements + lane * E;
+	const uint64_t warp_offset = (uint64_t) warp * Rows * row_elements + lane * E;
 
 	struct geometry_t { uint64_t segment, tile_in_segment, start, length; };
 	auto locate = [&](uint64_t tile) {
@@ -290,9 +290,9 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 		g.length = minimum(tile_elements, minimum(segment_length, length - segment_start) - offset);
 		return g;
 	};
-	auto request = [&](byte_pack<E * C> (&deltas)[look_back_rows], const geometry_t& g) {
+	auto request = [&](byte_pack<E * C> (&deltas)[Rows], const geometry_t& g) {
 		#pragma unroll
-		for (unsigned r = 0; r < look_back_rows; r++) {
+		for (unsigned r = 0; r < Rows; r++) {
 			const uint64_t p = warp_offset + r * row_elements;
 			if (p + E <= g.length) { deltas[r] = load_pack<E * C>(compressed_input + g.start + p); }
 			else {
@@ -303,10 +303,10 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 	};
 	// the warp's total first (one reduction): the tile's aggregate is published as early as possible and nothing but
 	// the deltas stays in registers across the look-back; the scans proper come afterwards
-	auto publish_warp_total = [&](const byte_pack<E * C> (&deltas)[look_back_rows], unsigned parity) {
+	auto publish_warp_total = [&](const byte_pack<E * C> (&deltas)[Rows], unsigned parity) {
 		uint_t<U> lane_total = 0;
 		#pragma unroll
-		for (unsigned r = 0; r < look_back_rows; r++) {
+		for (unsigned r = 0; r < Rows; r++) {
 			#pragma unroll
 			for (unsigned j = 0; j < E; j++) { lane_total = (uint_t<U>)(lane_total + (uint_t<U>) deltas[r].template get<C>(j)); }
 		}
@@ -337,9 +337,9 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 		}
 		return preceding_warps;
 	};
-	auto scan_and_store = [&](const byte_pack<E * C> (&deltas)[look_back_rows], const geometry_t& g, uint_t<U> carry) {
+	auto scan_and_store = [&](const byte_pack<E * C> (&deltas)[Rows], const geometry_t& g, uint_t<U> carry) {
 		#pragma unroll
-		for (unsigned r = 0; r < look_back_rows; r++) {
+		for (unsigned r = 0; r < Rows; r++) {
 			const uint64_t p = warp_offset + r * row_elements;
 			uint_t<U> local[E];
 			uint_t<U> sum = 0;
@@ -352,10 +352,11 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 			const uint_t<U> before = (uint_t<U>)(carry + (uint_t<U>)(inclusive - sum));
 			carry = (uint_t<U>)(carry + shuffle_from(inclusive, warp_size - 1));
 			if (E > 1 && p + E <= g.length) {
-				byte_pack<16> vec;
+				byte_pack<E * U> vec; // 16 bytes, or 32: one 256-bit store
 				#pragma unroll
 				for (unsigned j = 0; j < E; j++) { vec.template set<U>(j, (uint_t<U>)(before + local[j])); }
-				store_pack_16(decompressed + g.start + p, vec);
+				if constexpr (E * U == 32) { store_streaming_32(decompressed + g.start + p, vec.u32); }
+				else { store_streaming_16(decompressed + g.start + p, make_uint4(vec.u32[0], vec.u32[1], vec.u32[2], vec.u32[3])); }
 			}
 			else {
 				#pragma unroll
@@ -372,10 +373,10 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 		// then tile k is scanned and stored.
 		__shared__ uint_t<U> totals[3][32];   // [tile ordinal % 3]: written an iteration ahead, read in two iterations
 		__shared__ uint_t<U> exclusives[2];
-		auto publish_totals = [&](const byte_pack<E * C> (&deltas)[look_back_rows], unsigned slot) {
+		auto publish_totals = [&](const byte_pack<E * C> (&deltas)[Rows], unsigned slot) {
 			uint_t<U> lane_total = 0;
 			#pragma unroll
-			for (unsigned r = 0; r < look_back_rows; r++) {
+			for (unsigned r = 0; r < Rows; r++) {
 				#pragma unroll
 				for (unsigned j = 0; j < E; j++) { lane_total = (uint_t<U>)(lane_total + (uint_t<U>) deltas[r].template get<C>(j)); }
 			}
@@ -393,7 +394,7 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 		uint64_t tile = blockIdx.x;
 		if (tile >= num_tiles) { return; }
 		geometry_t g = locate(tile);
-		byte_pack<E * C> deltas[look_back_rows], next_deltas[look_back_rows];
+		byte_pack<E * C> deltas[Rows], next_deltas[Rows];
 		request(deltas, g);
 		publish_totals(deltas, 0);
 		__syncthreads();
@@ -432,7 +433,7 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 			GIDDY_DELTA_TRACE_POINT(tile, 5);
 			if (!has_next) { return; }
 			#pragma unroll
-			for (unsigned r = 0; r < look_back_rows; r++) { deltas[r] = next_deltas[r]; }
+			for (unsigned r = 0; r < Rows; r++) { deltas[r] = next_deltas[r]; }
 			tile = next_tile; g = next_g;
 		}
 	}
@@ -443,7 +444,7 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 			const uint64_t tile = shared_ticket[parity];
 			if (tile >= num_tiles) { return; }
 			const geometry_t g = locate(tile);
-			byte_pack<E * C> deltas[look_back_rows];
+			byte_pack<E * C> deltas[Rows];
 			request(deltas, g);
 			publish_warp_total(deltas, parity);
 			__syncthreads();
@@ -468,8 +469,15 @@ delta_decompress_long_segments(
 {
 	constexpr unsigned E = 16 / U;
 	const bool vectorizable = is_aligned_to(decompressed, 16) && is_aligned_to(compressed_input, E * C) && (segment_length % E == 0);
-	if (vectorizable) { delta_detail::decode_tiles_with_look_back<U, C, E, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
-	else              { delta_detail::decode_tiles_with_look_back<U, C, 1, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
+	// (a lane's piece of a row is 32 output bytes where alignment allows -- half the load, store and shuffle instructions
+	// per byte: the kernel is bound by the requests a multiprocessor can keep in flight -- else 16, else one element; the
+	// tile holds the same number of elements in the two vector shapes)
+	constexpr unsigned rows = delta_detail::look_back_rows;
+	static_assert(rows % 2 == 0, "a tile is also cut into rows of twice the width");
+	const bool vectorizable_32 = vectorizable && is_aligned_to(decompressed, 32) && is_aligned_to(compressed_input, 2 * E * C) && (segment_length % (2 * E) == 0);
+	if (vectorizable_32)   { delta_detail::decode_tiles_with_look_back<U, C, 2 * E, rows / 2, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
+	else if (vectorizable) { delta_detail::decode_tiles_with_look_back<U, C, E, rows, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
+	else                   { delta_detail::decode_tiles_with_look_back<U, C, 1, rows, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
 }
 
 } // namespace kernels

@@ -189,9 +189,9 @@ def test_policies_of_the_persistent_kernels(library):
     # 160 KB: all of it in shared memory
     c = resolve(library, S.dictionary_key(4, 4, 2), {"num_dictionary_entries": g.size_t(40000), "data_length": g.size_t(1 << 27)})
     assert (c.grid, c.block, c.dynamic_shared_memory_size) == (sms, 1024, 160000)
-    # Delta over one long segment: tiles + decoupled look-back, 3 CTAs of 256 threads per multiprocessor
+    # Delta over one long segment: tiles + decoupled look-back, 2 CTAs of 256 threads per multiprocessor
     c = resolve(library, S.delta_key(4, 8, 4), {"length": g.size_t(1 << 26), "segment_length": g.size_t(1 << 26)})
-    assert (c.grid, c.block, c.dynamic_shared_memory_size) == (3 * sms, 256, 0)
+    assert (c.grid, c.block, c.dynamic_shared_memory_size) == (2 * sms, 256, 0)
     # ... but anchored segments stay with a warp per segment
     c = resolve(library, S.delta_key(4, 8, 4), {"length": g.size_t(1 << 26), "segment_length": g.size_t(4096)})
     assert (c.grid, c.block) == ((1 << 14) // 8, 256)
