@@ -62,10 +62,11 @@ __device__ __forceinline__ void decode_segment(
 			const uint_t<U> before = (uint_t<U>)(carry + (uint_t<U>)(inclusive - sum));
 			carry = (uint_t<U>)(carry + shuffle_from(inclusive, warp_size - 1));
 			if (E > 1 && p + E <= length) {
-				byte_pack<16> vec;
+				byte_pack<E * U> vec; // 16 bytes, or 32: one 256-bit store
 				#pragma unroll
 				for (unsigned j = 0; j < E; j++) { vec.template set<U>(j, (uint_t<U>)(before + local[j])); }
-				store_pack_16(out + p, vec);
+				if constexpr (E * U == 32) { store_streaming_32(out + p, vec.u32); }
+				else { store_streaming_16(out + p, make_uint4(vec.u32[0], vec.u32[1], vec.u32[2], vec.u32[3])); }
 			}
 			else {
 				#pragma unroll
@@ -94,13 +95,17 @@ __global__ void delta_decompress(
 	const uint64_t num_segments = ((uint64_t) length + segment_length - 1) / segment_length;
 	const bool vectorizable = is_aligned_to(decompressed, 16) && is_aligned_to(compressed_input, E * C) &&
 		(segment_length % E == 0);
+	// (32 output bytes per lane per row where alignment allows: one 256-bit store, half the load and shuffle instructions per byte)
+	const bool vectorizable_32 = vectorizable && is_aligned_to(decompressed, 32) && is_aligned_to(compressed_input, 2 * E * C) &&
+		(segment_length % (2 * E) == 0);
 
 	for (uint64_t segment = global_warp_index(); segment < num_segments; segment += num_warps_in_grid()) {
 		const uint64_t start = segment * segment_length;
 		const uint64_t this_length = minimum<uint64_t>(segment_length, length - start);
 		const uint_t<U> anchor = __ldg(anchor_values + segment);
-		if (vectorizable) { delta_detail::decode_segment<U, C, E>(decompressed + start, compressed_input + start, this_length, anchor); }
-		else              { delta_detail::decode_segment<U, C, 1>(decompressed + start, compressed_input + start, this_length, anchor); }
+		if (vectorizable_32)   { delta_detail::decode_segment<U, C, 2 * E>(decompressed + start, compressed_input + start, this_length, anchor); }
+		else if (vectorizable) { delta_detail::decode_segment<U, C, E>(decompressed + start, compressed_input + start, this_length, anchor); }
+		else                   { delta_detail::decode_segment<U, C, 1>(decompressed + start, compressed_input + start, this_length, anchor); }
 	}
 }
 
