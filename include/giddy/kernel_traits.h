@@ -46,7 +46,7 @@
 #define GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR 2
 #endif
 #ifndef GIDDY_DELTA_LOOK_BACK_ROWS
-#define GIDDY_DELTA_LOOK_BACK_ROWS 16
+#define GIDDY_DELTA_LOOK_BACK_ROWS 24
 #endif
 #ifndef GIDDY_DELTA_LOOK_BACK_WINDOW
 #define GIDDY_DELTA_LOOK_BACK_WINDOW 4             /* descriptors inspected per lane per look-back round */
