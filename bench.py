@@ -541,12 +541,35 @@ def run_e2e(args, torch, np, g, columns, kernel, column, out, device, distribute
     return result
 
 
+class _quiet_stdout:
+    """stdout carries the one JSON line and nothing else: while the benchmark runs, file descriptor 1 points at stderr (NCCL
+    prints its version banner to fd 1 from C when the box sets NCCL_DEBUG), and Python-level prints are collected and
+    written to the real stdout at the end."""
+
+    def __enter__(self):
+        import io
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        self.python_stdout, sys.stdout = sys.stdout, io.StringIO()
+        return self
+
+    def __exit__(self, *exc):
+        collected, sys.stdout = sys.stdout.getvalue(), self.python_stdout
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        sys.stdout.write(collected)
+        sys.stdout.flush()
+        return False
+
+
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_product_arm(args)
+    with _quiet_stdout():
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_product_arm(args)
 
 
 if __name__ == "__main__":
