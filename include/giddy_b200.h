@@ -403,7 +403,11 @@ GIDDY_API giddy_status_t giddy_b200_patched_frame_of_reference_launch(
 
 typedef struct giddy_scan giddy_scan_t;
 
-/* A plan with `num_streams` side streams on the current device.  Operations are appended chunk by chunk (chunks are
+/* A scan object is not internally synchronised: build it and run it from one thread at a time (different scans may be
+ * used from different threads).  Pointers recorded in a plan (buffers, kernels) must stay valid for as long as it is
+ * replayed.
+ *
+ * A plan with `num_streams` side streams on the current device.  Operations are appended chunk by chunk (chunks are
  * created on first mention) and replayed in the order appended; chunk c runs on side stream c % num_streams. */
 GIDDY_API giddy_status_t giddy_scan_create(unsigned num_streams, giddy_scan_t** out);
 GIDDY_API void           giddy_scan_destroy(giddy_scan_t* scan);
