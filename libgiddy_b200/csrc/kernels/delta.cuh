@@ -357,10 +357,15 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 			const uint_t<U> before = (uint_t<U>)(carry + (uint_t<U>)(inclusive - sum));
 			carry = (uint_t<U>)(carry + shuffle_from(inclusive, warp_size - 1));
 			if (E > 1 && p + E <= g.length) {
-				byte_pack<E * U> vec; // 16 bytes, or 32: one 256-bit store
+				byte_pack<E * U> vec; // 16 bytes, or a multiple of 32: 256-bit stores
 				#pragma unroll
 				for (unsigned j = 0; j < E; j++) { vec.template set<U>(j, (uint_t<U>)(before + local[j])); }
-				if constexpr (E * U == 32) { store_streaming_32(decompressed + g.start + p, vec.u32); }
+				if constexpr (E * U >= 32) {
+					#pragma unroll
+					for (unsigned b = 0; b < E * U / 32; b++) {
+						store_streaming_32(reinterpret_cast<unsigned char*>(decompressed + g.start + p) + 32 * b, *reinterpret_cast<const uint32_t (*)[8]>(&vec.u32[8 * b]));
+					}
+				}
 				else { store_streaming_16(decompressed + g.start + p, make_uint4(vec.u32[0], vec.u32[1], vec.u32[2], vec.u32[3])); }
 			}
 			else {
@@ -477,10 +482,12 @@ delta_decompress_long_segments(
 	// (a lane's piece of a row is 32 output bytes where alignment allows -- half the load, store and shuffle instructions
 	// per byte: the kernel is bound by the requests a multiprocessor can keep in flight -- else 16, else one element; the
 	// tile holds the same number of elements in the two vector shapes)
+	// (wide pieces: at least 32 output bytes and, where the deltas are narrow, a whole 16-byte load of them)
 	constexpr unsigned rows = delta_detail::look_back_rows;
-	static_assert(rows % 2 == 0, "a tile is also cut into rows of twice the width");
-	const bool vectorizable_32 = vectorizable && is_aligned_to(decompressed, 32) && is_aligned_to(compressed_input, 2 * E * C) && (segment_length % (2 * E) == 0);
-	if (vectorizable_32)   { delta_detail::decode_tiles_with_look_back<U, C, 2 * E, rows / 2, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
+	constexpr unsigned wide = (16 / C > 2 * E) ? 16 / C : 2 * E; // elements of a wide piece
+	static_assert((rows * E) % wide == 0, "a tile is also cut into rows of wide pieces");
+	const bool vectorizable_32 = vectorizable && is_aligned_to(decompressed, 32) && is_aligned_to(compressed_input, wide * C) && (segment_length % wide == 0);
+	if (vectorizable_32)   { delta_detail::decode_tiles_with_look_back<U, C, wide, rows * E / wide, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
 	else if (vectorizable) { delta_detail::decode_tiles_with_look_back<U, C, E, rows, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
 	else                   { delta_detail::decode_tiles_with_look_back<U, C, 1, rows, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
 }
