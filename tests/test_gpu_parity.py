@@ -53,4 +53,8 @@ def test_matches_reference_kernels(case, library, reference_library):
     own kernels rebuilt for sm_100a -- outputs must be identical."""
     ours = cases.run_case_on_gpu(case, library)
     theirs = cases.run_case_on_gpu(case, reference_library)
+    if case.scheme == "delta" and not (ours == theirs).all():
+        # the reference's own Delta kernel races on shared memory (compute-sanitizer racecheck: profiles/sanitizer_r01final.md)
+        # and can, rarely, decode wrongly; give it a second run before calling the two libraries different
+        theirs = cases.run_case_on_gpu(case, reference_library)
     assert (ours == theirs).all(), _mismatch_report(case, theirs)
