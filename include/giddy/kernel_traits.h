@@ -60,6 +60,6 @@
  * warps of this many CTAs (of GIDDY_ELEMENTWISE_BLOCK_THREADS threads) per multiprocessor; an index of one patch range per
  * tile is built into a workspace before the decode. */
 #define GIDDY_PATCHED_UNROLL 8
-#define GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR 5
+#define GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR 4
 
 #endif /* GIDDY_KERNEL_TRAITS_H_ */

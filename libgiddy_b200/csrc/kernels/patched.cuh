@@ -178,89 +178,125 @@ __device__ __forceinline__ void decode_and_patch(
 	__shared__ uint4 stage_of_warp[max_warps_per_block][vectors_per_tile]; // 4 KiB per warp
 	uint4* const stage_vectors = stage_of_warp[warp_index_in_block()];
 
-	// (a warp takes tiles w, w + W, ...; each tile's patch range is requested an iteration ahead, so that the patches
-	// themselves can be requested together with the tile's compressed vectors: one memory round trip per tile, not two)
 	const uint64_t first_tile = global_warp_index(), tile_stride = num_warps_in_grid();
 	if (first_tile >= num_tiles) { return; }
-	patch_range_t<IndexSize> next_range = tile_ranges[first_tile];
-	#pragma unroll 1
-	for (index_t tile = (index_t) first_tile; ; ) {
-		const index_t tile_start = tile << log2_tile_elements;
-		const index_t tile_end = (index_t) minimum<uint64_t>((uint64_t) tile_start + elements_per_tile, length);
-		const patch_range_t<IndexSize> range = next_range;
-		const bool last_iteration = (uint64_t) tile + tile_stride >= num_tiles;
-		if (!last_iteration) { next_range = tile_ranges[tile + (index_t) tile_stride]; }
-		const index_t first_patch = range.first, past_last_patch = range.past_last;
-		const index_t num_patches = past_last_patch > first_patch ? past_last_patch - first_patch : 0; // uniform over the warp
 
-		if (vectorizable) {
-			const index_t first_vector = tile * vectors_per_tile;
-			const unsigned num_vectors = (unsigned)(tile_end / E - first_vector); // all of them but for the column's last tile
-			byte_pack<Decoder::in_bytes> in[unroll];
+	if (!vectorizable) { // misaligned buffers: element by element, patches stored after their elements
+		#pragma unroll 1
+		for (uint64_t tile = first_tile; tile < num_tiles; tile += tile_stride) {
+			const uint64_t tile_start = tile << log2_tile_elements;
+			const uint64_t tile_end = minimum<uint64_t>(tile_start + elements_per_tile, length);
+			const patch_range_t<IndexSize> range = tile_ranges[tile];
 			#pragma unroll
 			for (unsigned k = 0; k < unroll; k++) {
-				const unsigned v = k * warp_size + lane;
-				if (v < num_vectors) { in[k] = decoder.load(first_vector + v); }
-			}
-			uint_t<IndexSize> position = 0;
-			uint_t<U> value = 0;
-			if (lane < num_patches) { position = __ldg(patch_positions + first_patch + lane); value = __ldg(patch_values + first_patch + lane); }
-			if (num_patches != 0 && num_vectors == vectors_per_tile) {
-				// A patch stored to global memory after the vector which contains it is a partial write of a 32-byte
-				// sector: it merges in L2 (no HBM traffic) but each one still costs L2 a read-modify-write.  So the tile
-				// is patched BEFORE it is stored: through the warp's slice of shared memory, where a patch is a plain
-				// element store, and out again as whole vectors.
-				#pragma unroll
-				for (unsigned k = 0; k < unroll; k++) {
-					const byte_pack<16> out = decoder.decode(in[k], first_vector + k * warp_size + lane);
-					stage_vectors[k * warp_size + lane] = make_uint4(out.u32[0], out.u32[1], out.u32[2], out.u32[3]);
-				}
-				__syncwarp();
-				uint_t<U>* const stage_elements = reinterpret_cast<uint_t<U>*>(stage_vectors);
-				// (a position outside the tile can only come from a list which is not ascending: ignored, not written wild)
-				if (lane < num_patches && (index_t)(position - tile_start) < elements_per_tile) { stage_elements[(index_t)(position - tile_start)] = value; }
-				for (uint64_t q = (uint64_t) first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
-					const index_t in_tile = (index_t)(__ldg(patch_positions + q) - tile_start);
-					if (in_tile < elements_per_tile) { stage_elements[in_tile] = __ldg(patch_values + q); }
-				}
-				__syncwarp();
-				#pragma unroll
-				for (unsigned k = 0; k < unroll; k++) { store_streaming_16(decompressed + (uint64_t)(first_vector + k * warp_size + lane) * E, stage_vectors[k * warp_size + lane]); }
-				__syncwarp(); // the next tile's vectors go to the same slots
-			}
-			else {
-				#pragma unroll
-				for (unsigned k = 0; k < unroll; k++) {
-					const unsigned v = k * warp_size + lane;
-					if (v < num_vectors) { store_pack_16(decompressed + (uint64_t)(first_vector + v) * E, decoder.decode(in[k], first_vector + v)); }
-				}
-				// the column's < E trailing elements (in its last tile only)
-				const uint64_t i = (uint64_t)(first_vector + num_vectors) * E + lane;
-				if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
-				if (num_patches != 0) { // the column's last, partial tile: patches stored after their vectors
-					__syncwarp(); // orders the tile's stores before the patch stores
-					if (lane < num_patches) { decompressed[position] = value; }
-					for (uint64_t q = (uint64_t) first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
-						decompressed[__ldg(patch_positions + q)] = __ldg(patch_values + q);
-					}
-				}
-			}
-		}
-		else {
-			#pragma unroll
-			for (unsigned k = 0; k < unroll; k++) {
-				const uint64_t i = (uint64_t) tile_start + k * warp_size + lane;
+				const uint64_t i = tile_start + k * warp_size + lane;
 				if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
 			}
-			if (num_patches != 0) {
+			if (range.past_last > range.first) {
 				__syncwarp();
-				for (uint64_t q = (uint64_t) first_patch + lane; q < past_last_patch; q += warp_size) {
+				for (uint64_t q = (uint64_t) range.first + lane; q < range.past_last; q += warp_size) {
 					decompressed[__ldg(patch_positions + q)] = __ldg(patch_values + q);
 				}
 			}
 		}
-		if (last_iteration) { break; }
-		tile += (index_t) tile_stride;
+		return;
+	}
+
+	// A warp takes tiles w, w + W, ...  Two of them are in flight at any time: while tile t is decoded, patched and stored,
+	// the compressed vectors and the first 32 patches of tile t + W are on their way (and the patch range of tile t + 2W,
+	// which those requests will need) -- the kernel has registers for few warps, so each must keep more bytes in flight.
+	struct pending_t {
+		index_t                       tile;
+		patch_range_t<IndexSize>      range;
+		byte_pack<Decoder::in_bytes>  in[unroll];
+		uint_t<IndexSize>             position;
+		uint_t<U>                     value;
+	};
+	auto request = [&](pending_t& p) {
+		const index_t tile_start = p.tile << log2_tile_elements;
+		const index_t tile_end = (index_t) minimum<uint64_t>((uint64_t) tile_start + elements_per_tile, length);
+		const index_t first_vector = p.tile * vectors_per_tile;
+		const unsigned num_vectors = (unsigned)(tile_end / E - first_vector);
+		#pragma unroll
+		for (unsigned k = 0; k < unroll; k++) {
+			const unsigned v = k * warp_size + lane;
+			if (v < num_vectors) { p.in[k] = decoder.load(first_vector + v); }
+		}
+		p.position = 0; p.value = 0;
+		if (p.range.past_last > p.range.first && lane < p.range.past_last - p.range.first) {
+			p.position = __ldg(patch_positions + p.range.first + lane); p.value = __ldg(patch_values + p.range.first + lane);
+		}
+	};
+	auto finish = [&](const pending_t& p) {
+		const index_t tile_start = p.tile << log2_tile_elements;
+		const index_t tile_end = (index_t) minimum<uint64_t>((uint64_t) tile_start + elements_per_tile, length);
+		const index_t first_vector = p.tile * vectors_per_tile;
+		const unsigned num_vectors = (unsigned)(tile_end / E - first_vector); // all of them but for the column's last tile
+		const index_t first_patch = p.range.first, past_last_patch = p.range.past_last;
+		const index_t num_patches = past_last_patch > first_patch ? past_last_patch - first_patch : 0; // uniform over the warp
+		if (num_patches != 0 && num_vectors == vectors_per_tile) {
+			// A patch stored to global memory after the vector which contains it is a partial write of a 32-byte
+			// sector: it merges in L2 (no HBM traffic) but each one still costs L2 a read-modify-write.  So the tile
+			// is patched BEFORE it is stored: through the warp's slice of shared memory, where a patch is a plain
+			// element store, and out again as whole vectors.
+			#pragma unroll
+			for (unsigned k = 0; k < unroll; k++) {
+				const byte_pack<16> out = decoder.decode(p.in[k], first_vector + k * warp_size + lane);
+				stage_vectors[k * warp_size + lane] = make_uint4(out.u32[0], out.u32[1], out.u32[2], out.u32[3]);
+			}
+			__syncwarp();
+			uint_t<U>* const stage_elements = reinterpret_cast<uint_t<U>*>(stage_vectors);
+			// (a position outside the tile can only come from a list which is not ascending: ignored, not written wild)
+			if (lane < num_patches && (index_t)(p.position - tile_start) < elements_per_tile) { stage_elements[(index_t)(p.position - tile_start)] = p.value; }
+			for (uint64_t q = (uint64_t) first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
+				const index_t in_tile = (index_t)(__ldg(patch_positions + q) - tile_start);
+				if (in_tile < elements_per_tile) { stage_elements[in_tile] = __ldg(patch_values + q); }
+			}
+			__syncwarp();
+			#pragma unroll
+			for (unsigned k = 0; k < unroll; k++) { store_streaming_16(decompressed + (uint64_t)(first_vector + k * warp_size + lane) * E, stage_vectors[k * warp_size + lane]); }
+			__syncwarp(); // the next tile's vectors go to the same slots
+		}
+		else {
+			#pragma unroll
+			for (unsigned k = 0; k < unroll; k++) {
+				const unsigned v = k * warp_size + lane;
+				if (v < num_vectors) { store_pack_16(decompressed + (uint64_t)(first_vector + v) * E, decoder.decode(p.in[k], first_vector + v)); }
+			}
+			// the column's < E trailing elements (in its last tile only)
+			const uint64_t i = (uint64_t)(first_vector + num_vectors) * E + lane;
+			if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
+			if (num_patches != 0) { // the column's last, partial tile: patches stored after their vectors
+				__syncwarp(); // orders the tile's stores before the patch stores
+				if (lane < num_patches) { decompressed[p.position] = p.value; }
+				for (uint64_t q = (uint64_t) first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
+					decompressed[__ldg(patch_positions + q)] = __ldg(patch_values + q);
+				}
+			}
+		}
+	};
+
+	pending_t current, next;
+	current.tile = (index_t) first_tile;
+	current.range = tile_ranges[first_tile];
+	request(current);
+	bool has_next = first_tile + tile_stride < num_tiles;
+	patch_range_t<IndexSize> range_after = current.range;
+	if (has_next) { range_after = tile_ranges[first_tile + tile_stride]; }
+	#pragma unroll 1
+	while (true) {
+		bool has_after = false;
+		if (has_next) {
+			next.tile = current.tile + (index_t) tile_stride;
+			next.range = range_after;
+			request(next);
+			has_after = (uint64_t) next.tile + tile_stride < num_tiles;
+			if (has_after) { range_after = tile_ranges[next.tile + (index_t) tile_stride]; }
+		}
+		finish(current);
+		if (!has_next) { break; }
+		current = next;
+		has_next = has_after;
 	}
 }
 

@@ -195,8 +195,8 @@ def test_policies_of_the_persistent_kernels(library):
     # ... but anchored segments stay with a warp per segment
     c = resolve(library, S.delta_key(4, 8, 4), {"length": g.size_t(1 << 26), "segment_length": g.size_t(4096)})
     assert (c.grid, c.block) == ((1 << 14) // 8, 256)
-    # patched decoders: 5 CTAs of 256 threads per multiprocessor, warps striding over the tiles
+    # patched decoders: 4 CTAs of 256 threads per multiprocessor, warps striding over the tiles
     c = resolve(library, S.patched_dictionary_key(4, 8, 1), {"num_dictionary_entries": g.size_t(256), "data_length": g.size_t(1 << 29)})
-    assert (c.grid, c.block, c.dynamic_shared_memory_size) == (5 * sms, 256, 2048)
+    assert (c.grid, c.block, c.dynamic_shared_memory_size) == (4 * sms, 256, 2048)
     c = resolve(library, S.patched_dictionary_key(4, 8, 1), {"num_dictionary_entries": g.size_t(256), "data_length": g.size_t(5000)})
     assert c.grid == 2 and c.block == 256  # 5000 elements: two CTA tiles of 256 x 8 vectors x 2 elements
