@@ -35,9 +35,12 @@
 #define GIDDY_SCATTER_BLOCK_THREADS 256
 #define GIDDY_CI_SCATTER_WARPS_PER_BLOCK 4
 
-/* Delta: a lane scans this many rows of 16-byte vectors per step.  Columns with few, long segments (so that a warp per
- * segment could not fill the GPU) are decoded tile by tile with decoupled look-back instead: CTAs of this many threads,
- * tiles of threads * rows * (16 / U) elements, persistent CTAs fed by a ticket counter. */
+/* Delta: a lane scans this many rows of vectors per step (a warp per anchored segment).  Columns with few, long segments
+ * (so that a warp per segment could not fill the GPU) are decoded tile by tile with decoupled look-back instead: CTAs of
+ * GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS threads, tiles of threads * GIDDY_DELTA_LOOK_BACK_ROWS * (16 / U) elements, this many
+ * CTAs per multiprocessor, launched cooperatively with statically assigned tiles (a ticket counter where cooperative
+ * launches are not to be had).  The #ifndef guards let benchmarks/micro/lookback_probe.cu build the kernel under other
+ * settings. */
 #define GIDDY_DELTA_ROWS_PER_STEP 4
 #ifndef GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS
 #define GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS 256
