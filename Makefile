@@ -14,12 +14,12 @@ NVCC      ?= $(CUDA_HOME)/bin/nvcc
 CXX       := /usr/bin/g++
 
 ARCH_FLAGS := -gencode arch=compute_100a,code=sm_100a
-NVCC_FLAGS := -std=c++17 -O3 -lineinfo $(ARCH_FLAGS) -Xcompiler -fPIC,-fvisibility=hidden -Iinclude -Iinclude/giddy --expt-relaxed-constexpr -diag-suppress 186,1160
-CXX_FLAGS  := -std=c++17 -O2 -fPIC -fvisibility=hidden -Wall -Wextra -Wno-unused-parameter -Iinclude -Iinclude/giddy -I$(CUDA_HOME)/include
+NVCC_FLAGS := -std=c++17 -O3 -lineinfo $(ARCH_FLAGS) -Xcompiler -fPIC,-fvisibility=hidden -Iinclude -Iinclude/giddy --expt-relaxed-constexpr -diag-suppress 186,1160 $(EXTRA_DEFS)
+CXX_FLAGS  := -std=c++17 -O2 -fPIC -fvisibility=hidden -Wall -Wextra -Wno-unused-parameter -Iinclude -Iinclude/giddy -I$(CUDA_HOME)/include $(EXTRA_DEFS)
 
 SRC_DIR   := libgiddy_b200/csrc
-BUILD_DIR := build
-LIB_DIR   := libgiddy_b200/lib
+BUILD_DIR ?= build
+LIB_DIR   ?= libgiddy_b200/lib
 LIB       := $(LIB_DIR)/libgiddy_b200.so
 
 ABI_SRCS  := $(wildcard $(SRC_DIR)/abi/*.cu)
@@ -30,8 +30,19 @@ KERNEL_HDRS := $(wildcard $(SRC_DIR)/kernels/*.cuh) $(wildcard $(SRC_DIR)/abi/*.
 HOST_HDRS := $(wildcard include/giddy/*.hpp) $(wildcard include/giddy/*.h) $(wildcard include/giddy/*/*.hpp) $(wildcard include/giddy/*/*.h) include/giddy_b200.h
 
 ORACLE_LIB := oracle/libgiddy_oracle.so
+# The oracle doubles as the timed CPU baseline.  It is built in this container and travels to the GPU box as a binary, so it
+# cannot be -march=native (the box's host CPU may differ: an illegal instruction there would take the tests down with it);
+# x86-64-v3 (AVX2, BMI2, FMA) is the newest level both are sure to have.  bench.py rebuilds it -march=native on the box
+# it is timed on when a compiler is there (oracle/libgiddy_oracle_native.so).
+ORACLE_MARCH ?= x86-64-v3
 
-.PHONY: all lib oracle ref examples sass clean
+.PHONY: all lib oracle ref examples sass clean variant
+
+# A build of the whole library under other compile-time settings, for A/B measurements on the GPU box:
+#   make variant NAME=patched5 DEFS="-DGIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR=5"   -> benchmarks/variants/patched5/libgiddy_b200.so
+# (benchmarks load it with libgiddy_b200.Library(path); the .so is git-ignored but travels to the box)
+variant:
+	$(MAKE) lib BUILD_DIR=build/variants/$(NAME)/obj LIB_DIR=benchmarks/variants/$(NAME) EXTRA_DEFS="$(DEFS)"
 
 all: lib oracle
 
@@ -47,12 +58,12 @@ $(BUILD_DIR)/host/%.o: $(SRC_DIR)/host/%.cpp $(HOST_HDRS)
 
 $(LIB): $(ABI_OBJS) $(HOST_OBJS)
 	@mkdir -p $(LIB_DIR)
-	$(NVCC) $(ARCH_FLAGS) -shared -o $@ $^ -cudart static
+	$(NVCC) $(ARCH_FLAGS) -shared -o $@ $^ -cudart static -lpthread -ldl
 
 oracle: $(ORACLE_LIB)
 
 $(ORACLE_LIB): oracle/giddy_oracle.cpp
-	$(CXX) -std=c++17 -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -Wall -o $@ $<
+	$(CXX) -std=c++17 -O3 -march=$(ORACLE_MARCH) -fopenmp -fPIC -shared -Wall -o $@ $<
 
 ref:
 	bash oracle/build_ref.sh

@@ -63,6 +63,8 @@
  * warps of this many CTAs (of GIDDY_ELEMENTWISE_BLOCK_THREADS threads) per multiprocessor; an index of one patch range per
  * tile is built into a workspace before the decode. */
 #define GIDDY_PATCHED_UNROLL 8
+#ifndef GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR
 #define GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR 4
+#endif
 
 #endif /* GIDDY_KERNEL_TRAITS_H_ */

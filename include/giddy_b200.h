@@ -23,7 +23,8 @@
  *      The C++ wrapper classes (include/giddy/) call only these.  Each launcher
  *      cites the reference __global__ function it replaces.
  *
- *  (3) Fused composite decoders, (4) host-resident scans: see the section comments below.
+ *  (3) Fused composite decoders, (4) host-resident scans, (5) shard planning, (6) host memory placement,
+ *      (7) device groups: see the section comments below.
  *
  * Conventions: every function returns a giddy_status_t (0 = success) unless it
  * returns a pointer/count; on failure giddy_last_error() holds a message for the
@@ -446,6 +447,137 @@ GIDDY_API giddy_status_t giddy_scan_set_graph_replay(giddy_scan_t* scan, int ena
 /* Enqueue one scan: the side streams fork from `stream`, run their chunks, and are joined back into `stream`.
  * Asynchronous; the current device must be the one the scan was created on. */
 GIDDY_API giddy_status_t giddy_scan_run(giddy_scan_t* scan, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* (5) Shard planning: a contiguous range of anchored segments of a column as  */
+/* a self-contained column -- for the GPUs of a box, or the chunks of a        */
+/* host-resident scan.  No counterpart in the reference, which is single-GPU   */
+/* (src/kernel_wrappers/registered_wrapper.h:82); what makes it possible is    */
+/* the reference's own formats: every segment decodes from its anchor side     */
+/* data alone (run_length_encoding.cuh:284-325, discard_zero_bytes_variable    */
+/* .cuh:397-438, delta.cuh:80-92).  Planning reads host copies of the anchor   */
+/* arrays only; it never touches a device.                                     */
+/* ------------------------------------------------------------------------- */
+
+typedef enum giddy_scheme_t {
+	GIDDY_SCHEME_FRAME_OF_REFERENCE = 0, GIDDY_SCHEME_MODEL, GIDDY_SCHEME_RUN_LENGTH_ENCODING, GIDDY_SCHEME_RUN_POSITION_ENCODING,
+	GIDDY_SCHEME_DELTA, GIDDY_SCHEME_DICTIONARY, GIDDY_SCHEME_DISCARD_ZERO_BYTES_FIXED, GIDDY_SCHEME_DISCARD_ZERO_BYTES_VARIABLE,
+	GIDDY_SCHEME_INCIDENCE_BITMAPS, GIDDY_SCHEME_SCATTER
+} giddy_scheme_t;
+
+/* What the planner needs to know about a whole compressed column.  Array names below are the wrappers' argument names
+ * (SURVEY.md Appendix B).  Fields a scheme does not use are ignored. */
+typedef struct giddy_column_layout_t {
+	giddy_scheme_t scheme;
+	uint64_t       length;                 /* decompressed elements (SCATTER: length of the target column) */
+	uint64_t       segment_length;         /* anchoring period; for schemes without segments, the granularity shards are cut at */
+	unsigned       index_size;             /* bytes per element of the anchor array (RLE/RPE: RunIndexSize; DZB-variable: IndexSize; SCATTER: OutputIndexSize) */
+	unsigned       uncompressed_size;
+	unsigned       compressed_size;        /* FOR/Delta/DZB-fixed: Compressed; Dictionary: DictionaryIndexSize; RLE: RunLengthSize; RPE: PositionOffsetSize; DZB-variable: ElementSizesContainerSize */
+	unsigned       model_dimension;        /* FOR: coefficients per segment (1 constant, 2 linear) */
+	int            positions_are_relative; /* RPE */
+	unsigned       bits_per_element_size;  /* DZB-variable */
+	uint64_t       num_runs;               /* RLE/RPE: num_element_runs */
+	uint64_t       num_bytes;              /* DZB-variable: bytes of compressed_data */
+	unsigned       num_bitmaps;            /* incidence bitmaps */
+	unsigned       bitmap_alignment_in_ints;
+	uint64_t       num_patches;            /* SCATTER: data_length; indices must be ascending */
+	const void*    anchors;                /* HOST copy of position_anchors (RLE, RPE, DZB-variable); SCATTER: of indices */
+	const void*    run_start_positions;    /* HOST copy; RPE with relative positions only */
+} giddy_column_layout_t;
+
+/* A part of one of the column's arrays: `rows` rows of `count` elements starting at element `first`, `pitch` elements apart
+ * (rows == 1 but for incidence bitmaps).  Copied into a shard's own buffer, every element has `rebase` subtracted (anchors,
+ * absolute positions, target indices; elements smaller than `rebase` become 0 when `saturate` is set). */
+typedef struct giddy_slice_t {
+	const char* array;
+	uint64_t    first, count;
+	unsigned    element_size;
+	uint64_t    rows, pitch;
+	uint64_t    rebase;
+	int         saturate;
+} giddy_slice_t;
+
+#define GIDDY_MAX_SHARD_SLICES 6
+typedef struct giddy_shard_t {
+	uint64_t      first_segment, num_segments;
+	uint64_t      first_element, num_elements;  /* of the decompressed column; the shard's `length` */
+	uint64_t      num_runs;                     /* RLE/RPE: the shard's num_element_runs */
+	uint64_t      num_bytes;                    /* DZB-variable: the shard's bytes of compressed_data */
+	uint64_t      bitmap_length;                /* incidence bitmaps: containers per bitmap in the shard */
+	uint64_t      num_patches;                  /* SCATTER: the shard's data_length */
+	unsigned      num_slices;
+	giddy_slice_t slices[GIDDY_MAX_SHARD_SLICES];
+} giddy_shard_t;
+
+/* Segments [first, past_last) of part `part` of `parts` nearly equal contiguous parts of `num_segments`. */
+GIDDY_API giddy_status_t giddy_split_segments(uint64_t num_segments, unsigned parts, unsigned part, uint64_t* first, uint64_t* past_last);
+
+/* The slices of the column's arrays which segments [first_segment, past_last_segment) read, and the shard's scalar
+ * arguments.  GIDDY_INVALID_ARGUMENT when the range cannot stand on its own (a DZB-variable shard must begin on a
+ * size-container boundary). */
+GIDDY_API giddy_status_t giddy_shard_plan(const giddy_column_layout_t* column, uint64_t first_segment, uint64_t past_last_segment,
+	giddy_shard_t* out);
+
+/* Bytes of a slice once copied (rows * count * element_size), and the copy itself, host to host, rebasing on the way:
+ * `whole_array` is the column's array the slice was planned on, `destination` a buffer of the shard's own (e.g. pinned
+ * staging memory from giddy_host_alloc). */
+GIDDY_API size_t         giddy_slice_bytes(const giddy_slice_t* slice);
+GIDDY_API giddy_status_t giddy_slice_copy(const giddy_slice_t* slice, void* destination, const void* whole_array);
+
+/* Model: the coefficients of a shard which begins at element first_element: c0 + c1 * (first_element + i) = (c0 + c1 * first_element) + c1 * i,
+ * in the arithmetic of the model's coefficient type (coefficient_size bytes, signed). */
+GIDDY_API giddy_status_t giddy_shard_model_coefficients(const int64_t* coefficients, unsigned dimension, unsigned coefficient_size,
+	uint64_t first_element, int64_t* out);
+
+/* ------------------------------------------------------------------------- */
+/* (6) Host memory for host-resident columns: page-locked, and placed on the   */
+/* NUMA node the device hangs off, so that the GPUs of a box do not all pull   */
+/* their compressed chunks out of one socket's memory.                          */
+/* ------------------------------------------------------------------------- */
+
+/* The NUMA node of a CUDA device (sysfs), or -1 when the platform does not say (single-node hosts, containers). */
+GIDDY_API int giddy_host_numa_node_of_device(int device);
+
+/* `bytes` of page-locked host memory for copies to and from `device` (< 0: the current device): mapped, bound to the
+ * device's NUMA node where there is one (mbind), touched, and registered with CUDA (cudaHostRegisterPortable).
+ * *numa_node (optional) receives the node the memory was bound to, or -1. */
+GIDDY_API giddy_status_t giddy_host_alloc(size_t bytes, int device, void** out, int* numa_node);
+GIDDY_API giddy_status_t giddy_host_free(void* memory);
+
+/* Restrict the calling thread to the CPUs of the device's NUMA node (no-op returning -1 where there is none). */
+GIDDY_API int giddy_host_bind_thread_to_device(int device);
+
+/* ------------------------------------------------------------------------- */
+/* (7) Device groups: one worker thread per GPU of the box.  The decode path    */
+/* needs no collective; the one exchange of the multi-GPU path is the          */
+/* broadcast of a dictionary from the device which loaded it (NCCL over         */
+/* NVLink; libnccl is loaded on first use, never linked).                       */
+/* ------------------------------------------------------------------------- */
+
+typedef struct giddy_device_group giddy_device_group_t;
+
+/* A group over `devices[0 .. num_devices)` (NULL: all visible devices).  Each device gets a worker thread which makes
+ * the device current, binds itself to the device's NUMA node, and waits for work. */
+GIDDY_API giddy_status_t giddy_device_group_create(const int* devices, unsigned num_devices, giddy_device_group_t** out);
+GIDDY_API void           giddy_device_group_destroy(giddy_device_group_t* group);
+GIDDY_API unsigned       giddy_device_group_size(const giddy_device_group_t* group);
+GIDDY_API int            giddy_device_group_device(const giddy_device_group_t* group, unsigned rank);
+
+/* work(rank, group size, device, user_data) on every worker concurrently; returns when all have returned, with the
+ * first non-success status (and its message in giddy_last_error()). */
+typedef giddy_status_t (*giddy_device_work_t)(unsigned rank, unsigned num_devices, int device, void* user_data);
+GIDDY_API giddy_status_t giddy_device_group_run(giddy_device_group_t* group, giddy_device_work_t work, void* user_data);
+
+/* ncclBroadcast of `bytes` bytes from buffers[root] (on the root's device) to buffers[r] on every other device of the
+ * group, each on streams[r] (NULL: the devices' default streams); asynchronous on those streams.  Communicators are
+ * created on first use (ncclCommInitAll).  GIDDY_UNSUPPORTED when libnccl.so.2 cannot be loaded. */
+GIDDY_API giddy_status_t giddy_device_group_broadcast(giddy_device_group_t* group, void* const* buffers, size_t bytes, unsigned root,
+	void* const* streams);
+
+/* The same over a communicator of the caller's (one rank per process, e.g. under MPI): ncclBroadcast(buffer, buffer, bytes,
+ * ncclUint8, root, comm, stream). */
+GIDDY_API giddy_status_t giddy_broadcast_dictionary(void* nccl_communicator, void* buffer, size_t bytes, int root, void* stream);
 
 #ifdef __cplusplus
 } /* extern "C" */

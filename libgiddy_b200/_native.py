@@ -189,7 +189,72 @@ def load_library(path=_LIB_PATH):
         lib.giddy_scan_add_dependency.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_uint]
         lib.giddy_scan_set_graph_replay.argtypes = [ctypes.c_void_p, ctypes.c_int]
         lib.giddy_scan_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    if hasattr(lib, "giddy_shard_plan"):  # groups 5-7 (shard planning, host memory, device groups): the product only
+        lib.giddy_split_segments.argtypes = [ctypes.c_uint64, ctypes.c_uint, ctypes.c_uint, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+        lib.giddy_shard_plan.argtypes = [ctypes.POINTER(ColumnLayout), ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(Shard)]
+        lib.giddy_slice_bytes.argtypes = [ctypes.POINTER(Slice)]
+        lib.giddy_slice_bytes.restype = ctypes.c_size_t
+        lib.giddy_slice_copy.argtypes = [ctypes.POINTER(Slice), ctypes.c_void_p, ctypes.c_void_p]
+        lib.giddy_shard_model_coefficients.argtypes = [ctypes.POINTER(ctypes.c_int64), ctypes.c_uint, ctypes.c_uint, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int64)]
+        lib.giddy_host_numa_node_of_device.argtypes = [ctypes.c_int]
+        lib.giddy_host_bind_thread_to_device.argtypes = [ctypes.c_int]
+        lib.giddy_host_alloc.argtypes = [ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int)]
+        lib.giddy_host_free.argtypes = [ctypes.c_void_p]
+        lib.giddy_device_group_create.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p)]
+        lib.giddy_device_group_destroy.argtypes = [ctypes.c_void_p]
+        lib.giddy_device_group_destroy.restype = None
+        lib.giddy_device_group_size.argtypes = [ctypes.c_void_p]
+        lib.giddy_device_group_size.restype = ctypes.c_uint
+        lib.giddy_device_group_device.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+        lib.giddy_device_group_run.argtypes = [ctypes.c_void_p, DEVICE_WORK, ctypes.c_void_p]
+        lib.giddy_device_group_broadcast.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t, ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p)]
+        lib.giddy_broadcast_dictionary.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
     return lib
+
+
+# giddy_scheme_t
+(SCHEME_FRAME_OF_REFERENCE, SCHEME_MODEL, SCHEME_RUN_LENGTH_ENCODING, SCHEME_RUN_POSITION_ENCODING, SCHEME_DELTA, SCHEME_DICTIONARY,
+ SCHEME_DISCARD_ZERO_BYTES_FIXED, SCHEME_DISCARD_ZERO_BYTES_VARIABLE, SCHEME_INCIDENCE_BITMAPS, SCHEME_SCATTER) = range(10)
+
+
+class ColumnLayout(ctypes.Structure):
+    """giddy_column_layout_t: what the shard planner needs to know about a whole compressed column"""
+    _fields_ = [("scheme", ctypes.c_int), ("length", ctypes.c_uint64), ("segment_length", ctypes.c_uint64),
+                ("index_size", ctypes.c_uint), ("uncompressed_size", ctypes.c_uint), ("compressed_size", ctypes.c_uint),
+                ("model_dimension", ctypes.c_uint), ("positions_are_relative", ctypes.c_int), ("bits_per_element_size", ctypes.c_uint),
+                ("num_runs", ctypes.c_uint64), ("num_bytes", ctypes.c_uint64), ("num_bitmaps", ctypes.c_uint),
+                ("bitmap_alignment_in_ints", ctypes.c_uint), ("num_patches", ctypes.c_uint64),
+                ("anchors", ctypes.c_void_p), ("run_start_positions", ctypes.c_void_p)]
+
+
+class Slice(ctypes.Structure):
+    """giddy_slice_t"""
+    _fields_ = [("array", ctypes.c_char_p), ("first", ctypes.c_uint64), ("count", ctypes.c_uint64), ("element_size", ctypes.c_uint),
+                ("rows", ctypes.c_uint64), ("pitch", ctypes.c_uint64), ("rebase", ctypes.c_uint64), ("saturate", ctypes.c_int)]
+
+    @property
+    def name(self):
+        return self.array.decode()
+
+
+class Shard(ctypes.Structure):
+    """giddy_shard_t"""
+    _fields_ = [("first_segment", ctypes.c_uint64), ("num_segments", ctypes.c_uint64), ("first_element", ctypes.c_uint64),
+                ("num_elements", ctypes.c_uint64), ("num_runs", ctypes.c_uint64), ("num_bytes", ctypes.c_uint64),
+                ("bitmap_length", ctypes.c_uint64), ("num_patches", ctypes.c_uint64), ("num_slices", ctypes.c_uint), ("slices", Slice * 6)]
+
+    def slice(self, name):
+        for k in range(self.num_slices):
+            if self.slices[k].name == name:
+                return self.slices[k]
+        raise KeyError(name)
+
+    def names(self):
+        return [self.slices[k].name for k in range(self.num_slices)]
+
+
+# giddy_device_work_t
+DEVICE_WORK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_void_p)
 
 
 # giddy_scan_callback_t
@@ -473,7 +538,140 @@ class Library:
     def create_scan(self, num_streams=4):
         return Scan(self, num_streams)
 
+    # ---- group 5: shard planning --------------------------------------------------------------------------------
+
+    def split_segments(self, num_segments, parts, part):
+        first, past_last = ctypes.c_uint64(), ctypes.c_uint64()
+        self.check(self.lib.giddy_split_segments(int(num_segments), int(parts), int(part), ctypes.byref(first), ctypes.byref(past_last)))
+        return first.value, past_last.value
+
+    def shard_plan(self, layout, first_segment, past_last_segment):
+        shard = Shard()
+        self.check(self.lib.giddy_shard_plan(ctypes.byref(layout), int(first_segment), int(past_last_segment), ctypes.byref(shard)))
+        return shard
+
+    def slice_bytes(self, piece):
+        return self.lib.giddy_slice_bytes(ctypes.byref(piece))
+
+    def slice_copy(self, piece, destination, whole_array):
+        """destination, whole_array: host addresses, numpy arrays or CPU torch tensors"""
+        self.check(self.lib.giddy_slice_copy(ctypes.byref(piece), _address_of(destination), _address_of(whole_array)))
+
+    def shard_model_coefficients(self, coefficients, coefficient_size, first_element):
+        values = (ctypes.c_int64 * len(coefficients))(*[int(c) for c in coefficients])
+        out = (ctypes.c_int64 * len(coefficients))()
+        self.check(self.lib.giddy_shard_model_coefficients(values, len(coefficients), int(coefficient_size), int(first_element), out))
+        return list(out)
+
+    # ---- group 6: host memory ------------------------------------------------------------------------------------
+
+    def host_numa_node_of_device(self, device=-1):
+        node = self.lib.giddy_host_numa_node_of_device(int(device))
+        return None if node < 0 else node
+
+    def host_bind_thread_to_device(self, device=-1):
+        node = self.lib.giddy_host_bind_thread_to_device(int(device))
+        return None if node < 0 else node
+
+    def host_alloc(self, nbytes, device=-1):
+        """A HostBuffer: page-locked host memory on the device's NUMA node (where the platform has one)."""
+        return HostBuffer(self, nbytes, device)
+
+    # ---- group 7: device groups ----------------------------------------------------------------------------------
+
+    def create_device_group(self, devices=None):
+        return DeviceGroup(self, devices)
+
     def device_properties(self, device_id=-1):
         p = DeviceProperties()
         self.check(self.lib.giddy_device_properties(device_id, ctypes.byref(p)))
         return p
+
+
+class HostBuffer:
+    """giddy_host_alloc'd memory, viewable as a numpy array or a (CPU) torch tensor without copying."""
+
+    def __init__(self, library, nbytes, device=-1):
+        self._library, self.nbytes = library, int(nbytes)
+        pointer, node = ctypes.c_void_p(), ctypes.c_int(-1)
+        library.check(library.lib.giddy_host_alloc(self.nbytes, int(device), ctypes.byref(pointer), ctypes.byref(node)))
+        self.address = pointer.value or 0
+        self.numa_node = None if node.value < 0 else node.value
+
+    def numpy(self, dtype="uint8", offset=0, count=None):
+        import numpy as np
+        dtype = np.dtype(dtype)
+        count = (self.nbytes - offset) // dtype.itemsize if count is None else int(count)
+        if count == 0:
+            return np.empty(0, dtype)
+        buffer = (ctypes.c_ubyte * (count * dtype.itemsize)).from_address(self.address + offset)
+        array = np.frombuffer(buffer, dtype=dtype, count=count)
+        array.flags.writeable = True
+        return array
+
+    def tensor(self, dtype="uint8", offset=0, count=None):
+        import torch
+        array = self.numpy(dtype, offset, count)
+        if array.dtype.kind == "u" and array.dtype.itemsize > 1:
+            array = array.view("int%d" % (8 * array.dtype.itemsize))
+        return torch.from_numpy(array)
+
+    def free(self):
+        if self.address:
+            self._library.check(self._library.lib.giddy_host_free(self.address))
+            self.address = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceGroup:
+    """giddy_device_group_t: one worker thread per GPU; run(work) calls work(rank, size, device) on all of them at once."""
+
+    def __init__(self, library, devices=None):
+        self._library = library
+        handle = ctypes.c_void_p()
+        if devices is None:
+            library.check(library.lib.giddy_device_group_create(None, 0, ctypes.byref(handle)))
+        else:
+            array = (ctypes.c_int * len(devices))(*devices)
+            library.check(library.lib.giddy_device_group_create(array, len(devices), ctypes.byref(handle)))
+        self._handle = handle
+
+    def __del__(self):
+        if getattr(self, "_handle", None):
+            self._library.lib.giddy_device_group_destroy(self._handle)
+            self._handle = None
+
+    def __len__(self):
+        return self._library.lib.giddy_device_group_size(self._handle)
+
+    def device(self, rank):
+        return self._library.lib.giddy_device_group_device(self._handle, rank)
+
+    def run(self, work):
+        errors = []
+
+        def trampoline(rank, size, device, _user_data):
+            try:
+                work(rank, size, device)
+                return 0
+            except Exception as error:  # carried back to the caller's thread
+                errors.append(error)
+                return 7
+        callback = DEVICE_WORK(trampoline)
+        status = self._library.lib.giddy_device_group_run(self._handle, callback, None)
+        if errors:
+            raise errors[0]
+        self._library.check(status)
+
+    def broadcast(self, buffers, nbytes, root=0, streams=None):
+        """buffers: one device tensor / address per rank; the root's contents reach all the others (NCCL)."""
+        addresses = (ctypes.c_void_p * len(buffers))(*[_address_of(b) for b in buffers])
+        stream_array = None
+        if streams is not None:
+            stream_array = (ctypes.c_void_p * len(streams))(*[_stream_handle(s) for s in streams])
+        self._library.check(self._library.lib.giddy_device_group_broadcast(self._handle, addresses, int(nbytes), int(root), stream_array))

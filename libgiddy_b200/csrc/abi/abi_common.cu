@@ -47,6 +47,20 @@ static cudaError_t workspace_pool(cudaMemPool_t* pool)
 	return cudaSuccess;
 }
 
+cudaError_t static_shared_memory_of(const void* kernel, size_t* bytes)
+{
+	static thread_local std::map<const void*, size_t> known; // (a kernel's static shared memory is the same on every device)
+	auto it = known.find(kernel);
+	if (it == known.end()) {
+		cudaFuncAttributes attributes;
+		cudaError_t error = cudaFuncGetAttributes(&attributes, kernel);
+		if (error != cudaSuccess) { return error; }
+		it = known.emplace(kernel, attributes.sharedSizeBytes).first;
+	}
+	*bytes = it->second;
+	return cudaSuccess;
+}
+
 cudaError_t allocate_workspace(void** workspace, size_t bytes, cudaStream_t stream)
 {
 	cudaMemPool_t pool = nullptr;

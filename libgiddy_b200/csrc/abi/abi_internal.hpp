@@ -21,11 +21,20 @@ cudaError_t allocate_workspace(void** workspace, size_t bytes, cudaStream_t stre
 
 inline dim3 to_dim3(const unsigned (&d)[3]) { return dim3(d[0], d[1] ? d[1] : 1, d[2] ? d[2] : 1); }
 
-// Kernels which want more than the default 48 KiB of dynamic shared memory must opt in once per
-// function (and per device; the attribute is sticky, so re-applying is harmless).
+// A kernel may use 48 KiB of shared memory -- static plus dynamic -- without asking; beyond that it must opt in once per
+// function (and per device; the attribute is sticky, so re-applying is harmless).  The static part is a property of the
+// kernel (the patched decoders carry 33 KiB of it), asked of the runtime once per kernel and thread.
+cudaError_t static_shared_memory_of(const void* kernel, size_t* bytes);
+
 inline cudaError_t ensure_dynamic_shared_memory(const void* kernel, unsigned bytes)
 {
-	if (bytes <= 48 * 1024) { return cudaSuccess; }
+	if (bytes == 0) { return cudaSuccess; }
+	if (bytes <= 48 * 1024) {
+		size_t static_bytes = 0;
+		cudaError_t error = static_shared_memory_of(kernel, &static_bytes);
+		if (error != cudaSuccess) { return error; }
+		if (static_bytes + bytes <= 48 * 1024) { return cudaSuccess; }
+	}
 	return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
 }
 

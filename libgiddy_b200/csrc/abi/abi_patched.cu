@@ -31,7 +31,7 @@ template <unsigned I>
 size_t tile_index_bytes(uint64_t num_tiles) { return (size_t) num_tiles * sizeof(kernels::patched_detail::patch_range_t<I>); }
 
 template <unsigned I>
-giddy_status_t build_tile_index(cudaStream_t stream, void* ranges, const void* positions, uint64_t num_patches, unsigned log2_tile, uint64_t num_tiles)
+giddy_status_t build_tile_index(cudaStream_t stream, void* ranges, const void* positions, uint64_t num_patches, unsigned log2_tile, uint64_t num_tiles, uint64_t length)
 {
 	cudaError_t error = cudaMemsetAsync(ranges, 0, tile_index_bytes<I>(num_tiles), stream);
 	if (error != cudaSuccess) { return fail_cuda(error, "cudaMemsetAsync (patch tile index)"); }
@@ -39,7 +39,7 @@ giddy_status_t build_tile_index(cudaStream_t stream, void* ranges, const void* p
 	const unsigned threads = 256;
 	const uint64_t blocks = (num_patches + threads - 1) / threads;
 	kernels::patched_detail::patch_tile_ranges<I><<<(unsigned) (blocks < 0x7fffffffull ? blocks : 0x7fffffffull), threads, 0, stream>>>(
-		static_cast<kernels::patched_detail::patch_range_t<I>*>(ranges), static_cast<const uint_t<I>*>(positions), (size_type<I>) num_patches, log2_tile, num_tiles);
+		static_cast<kernels::patched_detail::patch_range_t<I>*>(ranges), static_cast<const uint_t<I>*>(positions), (size_type<I>) num_patches, log2_tile, length);
 	error = cudaGetLastError();
 	if (error != cudaSuccess) { return fail_cuda(error, "kernel launch (patch tile index)"); }
 	return GIDDY_SUCCESS;
@@ -55,7 +55,7 @@ giddy_status_t dict_launch(void* stream, const giddy_launch_config_t* cfg, void*
 	void* offsets = nullptr;
 	cudaError_t error = allocate_workspace(&offsets, tile_index_bytes<I>(num_tiles) + 16, s);
 	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocFromPoolAsync (patch tile index)"); }
-	giddy_status_t status = build_tile_index<I>(s, offsets, patch_indices, num_patches, log2_tile, num_tiles);
+	giddy_status_t status = build_tile_index<I>(s, offsets, patch_indices, num_patches, log2_tile, num_tiles, n);
 	if (status == GIDDY_SUCCESS) {
 		status = launch(kernels::patched_dictionary_decompress<I, U, DI>, stream, cfg,
 			static_cast<uint_t<U>*>(out), static_cast<const uint_t<DI>*>(in), static_cast<const uint_t<U>*>(dict),
@@ -102,6 +102,10 @@ giddy_status_t for_launch(void* stream, const giddy_launch_config_t* cfg, void* 
 	void* positions = static_cast<unsigned char*>(workspace) + offsets_bytes;
 	giddy_status_t status = GIDDY_SUCCESS;
 	if (data_length != 0) {
+		// (runs which cover fewer than data_length patches leave the rest of the list at positions beyond any column:
+		// never applied -- the reference's kernel would skip them too)
+		error = cudaMemsetAsync(positions, 0xff, data_length * I, s);
+		if (error != cudaSuccess) { cudaFreeAsync(workspace, s); return fail_cuda(error, "cudaMemsetAsync (patch positions)"); }
 		const uint64_t periods = (data_length + anchoring_period - 1) / anchoring_period;
 		const unsigned warps_per_block = GIDDY_CI_SCATTER_WARPS_PER_BLOCK;
 		const uint64_t blocks = (periods + warps_per_block - 1) / warps_per_block;
@@ -113,7 +117,7 @@ giddy_status_t for_launch(void* stream, const giddy_launch_config_t* cfg, void* 
 		error = cudaGetLastError();
 		if (error != cudaSuccess) { status = fail_cuda(error, "kernel launch (patch position decode)"); }
 	}
-	if (status == GIDDY_SUCCESS) { status = build_tile_index<I>(s, workspace, positions, data_length, log2_tile, num_tiles); }
+	if (status == GIDDY_SUCCESS) { status = build_tile_index<I>(s, workspace, positions, data_length, log2_tile, num_tiles, n); }
 	if (status == GIDDY_SUCCESS) {
 		status = launch(kernels::patched_frame_of_reference_decompress<I, U, C, M, MI>, stream, cfg,
 			static_cast<uint_t<U>*>(out), static_cast<const int_t<C>*>(in), static_cast<const int32_t*>(coeffs),

@@ -324,7 +324,10 @@ __device__ __forceinline__ void decode_segment_staged(
 		// the body of the byte range goes through TMA, its < 16 trailing bytes through four lanes
 		auto stage_bytes = [&](uint64_t past_last_byte) {
 			const uintptr_t first = reinterpret_cast<uintptr_t>(compressed_data) + tile_first_byte;
-			const uintptr_t past_last = reinterpret_cast<uintptr_t>(compressed_data) + past_last_byte;
+			// (a next anchor is a hint: whatever lies between it and the tile's last byte -- padding between segments, or
+			// a corrupt anchor -- is never decoded, so never staged either: a tile's elements occupy at most tile x U bytes)
+			const uintptr_t past_last = minimum<uintptr_t>(reinterpret_cast<uintptr_t>(compressed_data) + past_last_byte,
+				first + (uintptr_t) tile_elements * U);
 			const uintptr_t body_first = first & ~(uintptr_t) 15;
 			const uintptr_t body_past_last = (past_last & ~(uintptr_t) 15) > body_first ? (past_last & ~(uintptr_t) 15) : body_first;
 			const uint32_t body_bytes = (uint32_t)(body_past_last - body_first);

@@ -9,8 +9,8 @@
 // whatever the kernel does.  Storing the patch right after the vector which contains it, while the line is still
 // dirty in L2, saves the HBM traffic (measured: DRAM bytes = algorithmic bytes) but not the time: a partial-sector
 // write still costs L2 a read-modify-write, and three different kernel structures all ended at ~30 G patches/s.
-// Here a tile is therefore patched BEFORE it is stored, in the warp's slice of shared memory, and leaves the SM
-// as whole 16-byte vectors only.
+// Here a vector is therefore patched BEFORE it is stored, in the registers of the lane which decoded it, and leaves
+// the SM whole; shared memory only carries the routing information (which vectors are hit, by which patches).
 //
 // Requirement (the only one beyond the two schemes' own): patch positions are in ASCENDING order, as a
 // compressor which emits exceptions while scanning the column produces them.
@@ -25,10 +25,11 @@
 //                        neighbour in the list lies in another tile; the array starts out zeroed)
 // -- 8 bytes per tile (0.2-0.4 % of the output) plus, for compressed positions, 4 bytes per patch.  The decode
 // kernel then, per tile: (has its range, requested an iteration ahead) requests its compressed vectors and (lane l)
-// patch first + l, decodes the vectors into the warp's 4 KiB of shared memory, overwrites the patched elements
-// there, and stores whole vectors.  A tile without patches is stored straight from registers.
-// (A CTA-tile variant -- the stand-alone decoders' structure with a 16 KiB staging buffer and two barriers per
-// tile -- measured slower: profiles/patched_r01_notes.md.)
+// patch first + l; the lanes holding patches mark, in a 512-byte table of the warp's, the vectors they hit; every lane
+// reads its 8 marks with one load, decodes its vectors, replaces the patched elements in registers and stores whole
+// vectors.  (Round 1 parked all decoded vectors in 4 KiB of shared memory per warp and patched them there: 8 STS.128 +
+// 8 LDS.128 per lane and tile, mio_throttle among the top stalls, 33 KiB of static shared memory per CTA; a CTA-tile
+// variant with a 16 KiB staging buffer and two barriers per tile measured slower still: profiles/patched_r01_notes.md.)
 #pragma once
 #ifndef GIDDY_B200_KERNELS_PATCHED_CUH_
 #define GIDDY_B200_KERNELS_PATCHED_CUH_
@@ -43,6 +44,12 @@ namespace patched_detail {
 
 constexpr unsigned unroll = GIDDY_PATCHED_UNROLL;
 constexpr unsigned max_warps_per_block = GIDDY_ELEMENTWISE_BLOCK_THREADS / 32; // the launchers refuse larger blocks
+// CTAs per multiprocessor the kernels are compiled for: 64-bit indices, and dictionaries of 1- and 2-byte elements (8-16
+// lookups per vector), need more registers than the column shapes of 4- and 8-byte elements this is tuned for
+constexpr unsigned blocks_per_multiprocessor(unsigned index_size, unsigned element_size)
+{
+	return (index_size > 4 || element_size < 4) ? (GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR > 3 ? 3 : GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR) : GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR;
+}
 
 // ---- decoders ----------------------------------------------------------------------------------------
 // load(v): the compressed bytes of output vector v; decode(pack, v): its 16 decoded bytes;
@@ -128,11 +135,39 @@ struct frame_of_reference_decoder {
 	}
 };
 
+// out[element] = value for an element number known only at run time, with masks rather than a branch or an indexed
+// access per candidate (which the compiler turns into a round trip through local memory).
+template <unsigned U>
+__device__ __forceinline__ void replace_element(byte_pack<16>& out, unsigned element, uint_t<U> value)
+{
+	constexpr unsigned per_word = (U >= 4) ? 1 : 4 / U; // elements per 32-bit word
+	#pragma unroll
+	for (unsigned w = 0; w < 4; w++) {
+		uint32_t mask, bits;
+		if (U == 8) {
+			mask = (element == w / 2) ? 0xffffffffu : 0u;
+			bits = (w % 2) ? (uint32_t)((uint64_t) value >> 32) : (uint32_t) value;
+		}
+		else if (U == 4) {
+			mask = (element == w) ? 0xffffffffu : 0u;
+			bits = (uint32_t) value;
+		}
+		else {
+			const unsigned shift = (element % per_word) * 8 * U;
+			const uint32_t field = (U == 2) ? 0xffffu : 0xffu;
+			mask = (element / per_word == w) ? (field << shift) : 0u;
+			bits = (uint32_t) value << shift;
+		}
+		out.u32[w] = (out.u32[w] & ~mask) | (bits & mask);
+	}
+}
+
 // ---- the tile index -----------------------------------------------------------------------------------
 
 // ranges[t] = { first, past_last }: tile t's patches are [first, past_last) of the (ascending) patch list; tiles without
 // patches keep the zeroes the launcher filled the array with.  One thread per patch, no loops: patch j opens its tile's
-// range if its predecessor lies in an earlier tile and closes it if its successor lies in a later one.
+// range if its predecessor lies in an earlier tile and closes it if its successor lies in a later one.  Positions at or
+// beyond `length` (a list which is not what it should be) open and close nothing and are never applied.
 template <unsigned IndexSize>
 struct alignas(2 * sizeof(size_type<IndexSize>)) patch_range_t { size_type<IndexSize> first, past_last; };
 
@@ -142,11 +177,12 @@ __global__ void patch_tile_ranges(
 	const uint_t<IndexSize>*   __restrict__  positions,
 	size_type<IndexSize>                     num_patches,
 	unsigned                                 log2_tile_elements,
-	uint64_t                                 num_tiles)
+	uint64_t                                 length)
 {
 	for (uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; j < num_patches; j += (uint64_t) gridDim.x * blockDim.x) {
-		const uint64_t tile = (uint64_t) __ldg(positions + j) >> log2_tile_elements;
-		if (tile >= num_tiles) { continue; } // beyond the column: never applied
+		const uint64_t position = __ldg(positions + j);
+		if (position >= length) { continue; }
+		const uint64_t tile = position >> log2_tile_elements;
 		const bool opens = j == 0 || ((uint64_t) __ldg(positions + j - 1) >> log2_tile_elements) != tile;
 		const bool closes = j + 1 == num_patches || ((uint64_t) __ldg(positions + j + 1) >> log2_tile_elements) != tile;
 		if (opens) { ranges[tile].first = (size_type<IndexSize>) j; }
@@ -155,6 +191,18 @@ __global__ void patch_tile_ranges(
 }
 
 // ---- the tile loop -------------------------------------------------------------------------------------
+
+// What a warp keeps in shared memory to route a tile's patches to the lanes which own the patched vectors:
+//   slots[l * unroll + k]   for vector k * 32 + l of the tile (lane l's k-th vector): 1 + the index, within the tile's patch
+//                           range, of the first patch which falls into that vector, or 0 (16 bytes per lane: one LDS.128);
+//   positions / values      of the tile's first 32 patches (the ones requested ahead), position relative to the tile.
+// ~1 KiB per warp -- the decoded vectors themselves never leave the registers.
+template <unsigned IndexSize, unsigned U>
+struct alignas(16) patch_overlay_t {
+	uint16_t             slots[warp_size * unroll];
+	size_type<IndexSize> positions[warp_size];
+	uint_t<U>            values[warp_size];
+};
 
 template <unsigned IndexSize, unsigned U, typename Decoder>
 __device__ __forceinline__ void decode_and_patch(
@@ -169,14 +217,15 @@ __device__ __forceinline__ void decode_and_patch(
 	// registers -- for columns of up to 2^32 elements)
 	using index_t = size_type<IndexSize>;
 	constexpr unsigned E = Decoder::E;
+	static_assert(unroll == 8, "a lane's slots are read as one 16-byte vector of 8 x 16 bits");
 	uint_t<U>* __restrict__ const decompressed = decoder.decompressed;
 	const unsigned lane = lane_index();
 	const index_t elements_per_tile = (index_t) 1 << log2_tile_elements;
 	const bool vectorizable = elements_per_tile == (index_t)(warp_size * unroll * E) && decoder.vectorizable(); // (the launcher sized the tiles by the same test)
 	const index_t num_tiles = (index_t)(((uint64_t) length + elements_per_tile - 1) >> log2_tile_elements);
 	constexpr unsigned vectors_per_tile = warp_size * unroll;
-	__shared__ uint4 stage_of_warp[max_warps_per_block][vectors_per_tile]; // 4 KiB per warp
-	uint4* const stage_vectors = stage_of_warp[warp_index_in_block()];
+	__shared__ patch_overlay_t<IndexSize, U> overlay_of_warp[max_warps_per_block];
+	patch_overlay_t<IndexSize, U>& overlay = overlay_of_warp[warp_index_in_block()];
 
 	const uint64_t first_tile = global_warp_index(), tile_stride = num_warps_in_grid();
 	if (first_tile >= num_tiles) { return; }
@@ -195,7 +244,9 @@ __device__ __forceinline__ void decode_and_patch(
 			if (range.past_last > range.first) {
 				__syncwarp();
 				for (uint64_t q = (uint64_t) range.first + lane; q < range.past_last; q += warp_size) {
-					decompressed[__ldg(patch_positions + q)] = __ldg(patch_values + q);
+					const uint64_t position = __ldg(patch_positions + q);
+					// (a position outside the tile can only come from a list which is not ascending: ignored, not written wild)
+					if (position - tile_start < tile_end - tile_start) { decompressed[position] = __ldg(patch_values + q); }
 				}
 			}
 		}
@@ -234,28 +285,61 @@ __device__ __forceinline__ void decode_and_patch(
 		const unsigned num_vectors = (unsigned)(tile_end / E - first_vector); // all of them but for the column's last tile
 		const index_t first_patch = p.range.first, past_last_patch = p.range.past_last;
 		const index_t num_patches = past_last_patch > first_patch ? past_last_patch - first_patch : 0; // uniform over the warp
-		if (num_patches != 0 && num_vectors == vectors_per_tile) {
-			// A patch stored to global memory after the vector which contains it is a partial write of a 32-byte
-			// sector: it merges in L2 (no HBM traffic) but each one still costs L2 a read-modify-write.  So the tile
-			// is patched BEFORE it is stored: through the warp's slice of shared memory, where a patch is a plain
-			// element store, and out again as whole vectors.
+		if (num_vectors == vectors_per_tile) {
+			// A patch stored to global memory after the vector which contains it is a partial write of a 32-byte sector:
+			// it merges in L2 (no HBM traffic) but each one still costs L2 a read-modify-write.  So a vector is patched
+			// BEFORE it is stored, in the registers of the lane which owns it.  What that lane needs to know -- which of its
+			// vectors are hit, and by which patches -- goes through the warp's overlay: the lanes holding the patches mark
+			// the slot of the vector they hit, every lane reads its 8 slots with one 16-byte load.  Patches are ascending,
+			// so those of one vector are neighbours in the list: only the first of them marks the slot, and the owner walks
+			// on from there.
+			uint4 my_slots = make_uint4(0u, 0u, 0u, 0u);
+			if (num_patches != 0) {
+				reinterpret_cast<uint4*>(overlay.slots)[lane] = my_slots;
+				__syncwarp();
+				// (a position outside the tile can only come from a list which is not ascending: ignored, not written wild)
+				index_t in_tile = (index_t)(p.position - tile_start);
+				bool valid = lane < num_patches && in_tile < elements_per_tile;
+				if (!valid) { in_tile = ~(index_t) 0; }
+				unsigned vector = (unsigned)(in_tile / E);
+				overlay.positions[lane] = in_tile;
+				overlay.values[lane] = p.value;
+				unsigned previous = __shfl_up_sync(full_mask, vector, 1);
+				if (valid && (lane == 0 || previous != vector)) { overlay.slots[(vector % warp_size) * unroll + vector / warp_size] = (uint16_t)(lane + 1); }
+				// tiles with more than 32 patches: the rest of the list, 32 at a time (their owners will fetch them from global memory)
+				for (index_t base = warp_size; base < num_patches; base += warp_size) {
+					const unsigned carried = __shfl_sync(full_mask, vector, warp_size - 1);
+					const index_t q = base + lane;
+					in_tile = ~(index_t) 0;
+					if (q < num_patches) { in_tile = (index_t)(__ldg(patch_positions + first_patch + q) - tile_start); }
+					valid = in_tile < elements_per_tile;
+					vector = valid ? (unsigned)(in_tile / E) : ~0u;
+					previous = __shfl_up_sync(full_mask, vector, 1);
+					if (lane == 0) { previous = carried; }
+					if (valid && previous != vector && q < 0xffffu) { overlay.slots[(vector % warp_size) * unroll + vector / warp_size] = (uint16_t)(q + 1); }
+				}
+				__syncwarp();
+				my_slots = reinterpret_cast<const uint4*>(overlay.slots)[lane];
+			}
+			const uint32_t slot_words[4] = { my_slots.x, my_slots.y, my_slots.z, my_slots.w };
 			#pragma unroll
 			for (unsigned k = 0; k < unroll; k++) {
-				const byte_pack<16> out = decoder.decode(p.in[k], first_vector + k * warp_size + lane);
-				stage_vectors[k * warp_size + lane] = make_uint4(out.u32[0], out.u32[1], out.u32[2], out.u32[3]);
+				byte_pack<16> out = decoder.decode(p.in[k], first_vector + k * warp_size + lane);
+				const unsigned slot = (slot_words[k / 2] >> (16 * (k % 2))) & 0xffffu;
+				if (slot != 0) {
+					const unsigned my_vector = k * warp_size + lane;
+					index_t q = slot - 1;
+					do {
+						const index_t in_tile = q < warp_size ? overlay.positions[q] : (index_t)(__ldg(patch_positions + first_patch + q) - tile_start);
+						if (in_tile / E != my_vector) { break; }
+						const uint_t<U> value = q < warp_size ? overlay.values[q] : __ldg(patch_values + first_patch + q);
+						replace_element<U>(out, (unsigned)(in_tile % E), value);
+						q++;
+					} while (q < num_patches);
+				}
+				store_pack_16(decompressed + (uint64_t)(first_vector + k * warp_size + lane) * E, out);
 			}
-			__syncwarp();
-			uint_t<U>* const stage_elements = reinterpret_cast<uint_t<U>*>(stage_vectors);
-			// (a position outside the tile can only come from a list which is not ascending: ignored, not written wild)
-			if (lane < num_patches && (index_t)(p.position - tile_start) < elements_per_tile) { stage_elements[(index_t)(p.position - tile_start)] = p.value; }
-			for (uint64_t q = (uint64_t) first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
-				const index_t in_tile = (index_t)(__ldg(patch_positions + q) - tile_start);
-				if (in_tile < elements_per_tile) { stage_elements[in_tile] = __ldg(patch_values + q); }
-			}
-			__syncwarp();
-			#pragma unroll
-			for (unsigned k = 0; k < unroll; k++) { store_streaming_16(decompressed + (uint64_t)(first_vector + k * warp_size + lane) * E, stage_vectors[k * warp_size + lane]); }
-			__syncwarp(); // the next tile's vectors go to the same slots
+			if (num_patches != 0) { __syncwarp(); } // the next tile's patches go to the same overlay
 		}
 		else {
 			#pragma unroll
@@ -268,9 +352,10 @@ __device__ __forceinline__ void decode_and_patch(
 			if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
 			if (num_patches != 0) { // the column's last, partial tile: patches stored after their vectors
 				__syncwarp(); // orders the tile's stores before the patch stores
-				if (lane < num_patches) { decompressed[p.position] = p.value; }
+				if (lane < num_patches && (index_t)(p.position - tile_start) < tile_end - tile_start) { decompressed[p.position] = p.value; }
 				for (uint64_t q = (uint64_t) first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
-					decompressed[__ldg(patch_positions + q)] = __ldg(patch_values + q);
+					const index_t position = __ldg(patch_positions + q);
+					if ((index_t)(position - tile_start) < tile_end - tile_start) { decompressed[position] = __ldg(patch_values + q); }
 				}
 			}
 		}
@@ -310,7 +395,7 @@ __device__ __forceinline__ void decode_and_patch(
 // patch_indices must be ascending.
 // -------------------------------------------------------------------------------------------------
 template <unsigned IndexSize, unsigned U, unsigned DictionaryIndexSize>
-__global__ void __launch_bounds__(GIDDY_ELEMENTWISE_BLOCK_THREADS, GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR) patched_dictionary_decompress(
+__global__ void __launch_bounds__(GIDDY_ELEMENTWISE_BLOCK_THREADS, patched_detail::blocks_per_multiprocessor(IndexSize, U)) patched_dictionary_decompress(
 	uint_t<U>*                          __restrict__  decompressed,
 	const uint_t<DictionaryIndexSize>*  __restrict__  compressed_input,
 	const uint_t<U>*                    __restrict__  dictionary_entries,
@@ -337,7 +422,7 @@ __global__ void __launch_bounds__(GIDDY_ELEMENTWISE_BLOCK_THREADS, GIDDY_PATCHED
 // patch list.
 // -------------------------------------------------------------------------------------------------
 template <unsigned IndexSize, unsigned U, unsigned C, int Model, unsigned ModelIndexSize>
-__global__ void __launch_bounds__(GIDDY_ELEMENTWISE_BLOCK_THREADS, GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR) patched_frame_of_reference_decompress(
+__global__ void __launch_bounds__(GIDDY_ELEMENTWISE_BLOCK_THREADS, patched_detail::blocks_per_multiprocessor(IndexSize, U)) patched_frame_of_reference_decompress(
 	uint_t<U>*                   __restrict__  decompressed,
 	const int_t<C>*              __restrict__  compressed_input,
 	const int32_t*               __restrict__  segment_model_coefficients,
