@@ -42,7 +42,7 @@ ORACLE_MARCH ?= x86-64-v3
 #   make variant NAME=patched5 DEFS="-DGIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR=5"   -> benchmarks/variants/patched5/libgiddy_b200.so
 # (benchmarks load it with libgiddy_b200.Library(path); the .so is git-ignored but travels to the box)
 variant:
-	$(MAKE) lib BUILD_DIR=build/variants/$(NAME)/obj LIB_DIR=benchmarks/variants/$(NAME) EXTRA_DEFS="$(DEFS)"
+	$(MAKE) -j8 lib BUILD_DIR=build/variants/$(NAME)/obj LIB_DIR=benchmarks/variants/$(NAME) EXTRA_DEFS="$(DEFS)"
 
 all: lib oracle
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the headline benchmark of the decompression path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--configs cfg1,cfg3,...|none]
 
 Workload (BASELINE.json configs[1]): Run-Length Encoding, uint32 values + uint16 run lengths, 2^30
 decompressed elements per GPU, run lengths uniform in {1..31} (mean 16), anchored segments of 1024
@@ -15,7 +15,14 @@ Prints ONE JSON line (rank 0):
             against the measured copy bandwidth in MEASURED_PEAKS.json
   e2e       the same metric from pinned HOST buffers: the compressed column is copied H2D in segment-range
             chunks on side streams, each chunk decoded as it lands, and a sample of every chunk's output
-            is read back D2H; all inside the timed region
+            is read back D2H (e2e.value: the decompressed column stays in HBM for a GPU consumer);
+            e2e.result_returning is the same with every chunk's WHOLE output copied back to pinned host
+            memory, overlapped with the next chunks (for a host consumer); both with their measured
+            raw-copy ceilings; all inside the timed region
+  configs   every other BASELINE.json configuration at its named shape (benchmarks/configs.py), timed in
+            this process after the headline: ms, algorithmic bytes, fraction of the HBM roofline,
+            bit-exactness, the reference's own kernels beside it; under torchrun also ONE column split
+            into segment-range shards over the GPUs (strong scaling)
   cpu_baseline  the oracle's scalar host decoder (OpenMP, all host threads) on a bounded sample
 With --impl reference the CPU decoder alone is timed (the reference ships no CPU path; its kernels
 are GPU-only, so the "reference arm" of this tier is the host decoder written from its format).
@@ -38,6 +45,7 @@ LOG2_N = 30
 SEGMENT_LENGTH = 1024
 MAX_RUN = 31
 KEY = "decompression::run_length_encoding::kernel_t<4u, 4u, 2u, 4u>"
+ORACLE_MARCH = None
 
 
 def parse_args():
@@ -54,6 +62,8 @@ def parse_args():
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-verify", action="store_true")
+    p.add_argument("--configs", default="cfg1,cfg3,cfg4,cfg5", help="BASELINE configurations timed after the headline (comma-separated, or 'none')")
+    p.add_argument("--configs-repeats", type=int, default=10)
     return p.parse_args()
 
 
@@ -206,6 +216,9 @@ def host_sample(np, log2_elements, segment_length, seed):
 def time_host_decoder(np, sample, segment_length, passes, seconds=None):
     """Decode the sample `passes` times -- or, with `seconds`, as many times as fit (at least 3, at most 400)."""
     from oracle import giddy_oracle as O  # the checker / CPU baseline: the only use of oracle/ in this file
+    global ORACLE_MARCH
+    if ORACLE_MARCH is None:
+        ORACLE_MARCH = O.use_native_build()  # SURVEY 8d: -O3 -march=native on the box it is timed on
     # all the host threads this process may use -- torchrun exports OMP_NUM_THREADS=1, which would leave the decoder on one core
     O.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     out = np.empty(sample["n"], dtype=np.uint32)
@@ -240,16 +253,18 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "decompressed GB/s", "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": workload_config(args, sample_note="each step decodes a bounded sample: " + description),
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": "port", "sample": description},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": "port", "sample": "each step decodes a bounded sample: " + description,
+                         "march": ORACLE_MARCH},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference (eyalroz/libgiddy) has no CPU implementation; this is the scalar host decoder written from its format "
                 "definitions (oracle/giddy_oracle.cpp), OpenMP over segments, on the box's host threads",
     }))
 
 
-def workload_config(args, sample_note=None):
-    config = {
+def workload_config(args):
+    # (key for key the same in both arms: the driver compares them)
+    return {
         "workload": "RLE decode: uint32 values + uint16 run lengths, 2^%d decompressed elements per GPU, run lengths uniform {1..31} (mean 16), "
                     "anchored segments of %d elements (BASELINE.json configs[1])" % (args.log2_n, args.segment_length),
         "factory_key": KEY,
@@ -257,9 +272,6 @@ def workload_config(args, sample_note=None):
         "cache": "working set per step (4.7 GB) is far larger than the 126 MB L2; no flush needed",
         "parallelism": "segment ranges / columns sharded over GPUs, no data-path collective",
     }
-    if sample_note:
-        config["sample"] = sample_note
-    return config
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -280,10 +292,6 @@ def run_product_arm(args):
         raise SystemExit("bench.py needs a CUDA device: libgiddy_b200 has no CPU path (use --impl reference for the host decoder)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    numa_node = None
-    if distributed:  # pinned buffers of the host-resident leg should live on the socket this rank's GPU hangs off
-        from libgiddy_b200 import hostmem
-        numa_node = hostmem.bind_to_numa_node_of_gpu(local_rank)
     if distributed:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -291,6 +299,9 @@ def run_product_arm(args):
         dist.init_process_group("nccl", device_id=device)
 
     library = g.default_library()
+    # pinned buffers of the host-resident leg live on the NUMA node this rank's GPU hangs off (giddy_host_alloc), and so does
+    # the thread which submits the copies; None where the platform reports no node
+    numa_node = library.host_bind_thread_to_device(local_rank) if distributed else library.host_numa_node_of_device(local_rank)
     kernel = library.produce_subclass(KEY)
     n, L = 1 << args.log2_n, args.segment_length
     column, lengths64 = synthesize_rle_column(torch, n, L, 1234 + rank, device)
@@ -373,7 +384,7 @@ def run_product_arm(args):
 
     e2e = None
     if not args.skip_e2e:
-        e2e = run_e2e(args, torch, np, g, columns, kernel, column, out, device, distributed, world)
+        e2e = run_e2e(args, torch, np, g, columns, library, kernel, column, out, device, distributed, world)
     clocks = sampler.summary(t_begin, t_end) if rank == 0 else None
     sampler.stop()
 
@@ -386,11 +397,18 @@ def run_product_arm(args):
         sample = host_sample(np, args.cpu_sample_log2, L, 3)
         times, threads = time_host_decoder(np, sample, L, 0, seconds=args.cpu_seconds)
         timed = times[1:]
-        cpu_baseline = {"value": sample["n"] * 4 * len(timed) / sum(timed) / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+        cpu_baseline = {"value": sample["n"] * 4 * len(timed) / sum(timed) / 1e9, "unit": "GB/s", "cores": threads, "kind": "port", "march": ORACLE_MARCH,
                         "best_pass_value": sample["n"] * 4 / min(timed) / 1e9,
                         "sample": "2^%d elements of the same distribution (run lengths U{1..31}, L=%d) decoded %d times after one warm-up pass: "
                                   "%.1f s of host time; scalar C++ host decoder (oracle/giddy_oracle.cpp), OpenMP over segments" % (
                                       args.cpu_sample_log2, L, len(timed), sum(times))}
+
+    # every other BASELINE configuration, in this process, after the headline (all ranks together under torchrun)
+    configs = None
+    if args.configs and args.configs != "none":
+        del column, out, launch_arguments
+        torch.cuda.empty_cache()
+        configs = run_configs_block(args, torch, g, library, device, world, rank)
 
     if rank == 0:
         print(json.dumps({
@@ -398,7 +416,7 @@ def run_product_arm(args):
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "verified_bit_exact": verified,
-            "reference_kernels": reference_kernels, "numa_node_rank0": numa_node,
+            "reference_kernels": reference_kernels, "numa_node_rank0": numa_node, "configs": configs,
             "algorithmic_gbs_all_gpus": algorithmic_total * args.steps / seconds / 1e9,
             "library": library.version(),
         }))
@@ -436,41 +454,114 @@ def time_reference_kernels(args, torch, g, column, out, resolve_arguments, launc
         return {"unavailable": str(error)[:200]}
 
 
-def run_e2e(args, torch, np, g, columns, kernel, column, out, device, distributed, world):
-    """Host-resident mode: pinned compressed column -> chunked H2D on side streams -> decode per chunk -> D2H sample."""
+def run_configs_block(args, torch, g, library, device, world, rank):
+    """BASELINE configs[0], [2], [3], [4] (and, on several GPUs, one column split by segment range) through
+    benchmarks/configs.py: same process, same library, after the headline."""
+    from benchmarks import configs as C
+    C.LOG_FILE = sys.stderr
+    names = [name for name in args.configs.split(",") if name in C.CONFIGS]
+    if world > 1 and "strong" not in names:
+        names.append("strong")
+    reference = None
+    path = os.path.join(ROOT, "oracle", "_ref", "libgiddy_ref.so")
+    if os.path.exists(path) and not args.skip_reference_kernels:
+        reference = g.Library(path)
+    options = C.Options(shrink=LOG2_N - args.log2_n if args.log2_n < LOG2_N else 0, repeats=args.configs_repeats)
+    try:
+        rows = C.run_configs(names, options, device, library, reference)
+    except Exception as error:  # a failed side measurement must not cost the headline
+        if world > 1:
+            raise
+        return {"failed": str(error)[:300]}
+    keep = ("config", "chain", "ms", "decompressed_gbs", "algorithmic_gbs", "algorithmic_bytes_per_gpu", "frac_of_measured_peak_per_gpu", "bit_exact",
+            "reference_kernels_ms", "speedup_vs_reference_kernels", "extension", "scaling", "whole_column_decompressed_gbs", "h2d_gbs_per_gpu",
+            "gain_over_uncompressed_copy", "compression_ratio", "uncompressed_copy_gbs")
+    return {"repeats": args.configs_repeats, "timing": "CUDA events around `repeats` back-to-back passes after 3 warm-ups, max over ranks; working sets >> L2",
+            "frac": "algorithmic bytes / time / MEASURED_PEAKS.json hbm_gbs, per GPU", "all_bit_exact": all(bool(r["bit_exact"]) for r in rows),
+            "rows": [{k: r[k] for k in keep if k in r} for r in rows]}
+
+
+def run_e2e(args, torch, np, g, columns, library, kernel, column, out, device, distributed, world):
+    """Host-resident mode.  The compressed column lives in pinned host memory in CHUNK-MAJOR form: for each of 16 segment
+    ranges, the slices that range reads -- run values, run lengths, anchors rebased to its first run, intra-run offsets
+    -- back to back in one giddy_host_alloc buffer (written once, untimed, by the library's planner: giddy_shard_plan +
+    giddy_slice_copy).  A pass = per chunk ONE H2D copy, one decode launch, and the copy back of (a) a sample of the
+    chunk's output or (b) all of it; chunks go round-robin over 4 side streams; planned once and replayed by the
+    library's scan executor (giddy_scan_run)."""
+    from libgiddy_b200 import _native as N
     n, L, S, R = column["n"], column["segment_length"], column["num_segments"], column["num_runs"]
-    host = {k: column[k].cpu().pin_memory() for k in ("run_data", "run_lengths", "position_anchors", "intra_run_anchor_offsets")}
-    anchors_np = host["position_anchors"].numpy()
-    dev = {k: torch.empty_like(column[k]) for k in host}  # in-place placement: absolute run indices stay valid
+    names = ("run_data", "run_lengths", "position_anchors", "intra_run_anchor_offsets")
+    whole = {k: column[k].cpu().numpy() for k in names}
+    whole = {k: (v.view("uint%d" % (8 * v.dtype.itemsize))) for k, v in whole.items()}
     num_chunks, num_streams, sample_elements = 16, 4, 16384
-    chunks = [columns.RunLengthShard(anchors_np, s0, s1, L, n, R) for (s0, s1) in columns.split_segments(S, num_chunks)]
-    samples = torch.empty((num_chunks, sample_elements), dtype=torch.int32).pin_memory()
-    h2d_bytes = sum(c.num_runs * 6 + (c.s1 - c.s0) * 6 for c in chunks)
+    layout = columns._layout(N.SCHEME_RUN_LENGTH_ENCODING, n, L, index_size=4, uncompressed_size=4, compressed_size=2, num_runs=R,
+                             anchors=whole["position_anchors"])
+    shards = [library.shard_plan(layout, *library.split_segments(S, num_chunks, c)) for c in range(num_chunks)]
+
+    def aligned(x):
+        return (x + 255) // 256 * 256
+    placements, total = [], 0  # per chunk: {array name: (byte offset in the packed buffer, bytes)}
+    for shard in shards:
+        placement = {}
+        for k in range(shard.num_slices):
+            piece = shard.slices[k]
+            placement[piece.name] = (total, library.slice_bytes(piece))
+            total = aligned(total + library.slice_bytes(piece))
+        placements.append(placement)
+    host_packed = library.host_alloc(total, device.index)  # on the GPU's NUMA node where there is one
+    for shard, placement in zip(shards, placements):
+        for k in range(shard.num_slices):
+            piece = shard.slices[k]
+            library.slice_copy(piece, host_packed.address + placement[piece.name][0], whole[piece.name])
+    del whole
+    dev_packed = torch.empty(total, dtype=torch.uint8, device=device)
+    samples_buffer = library.host_alloc(num_chunks * sample_elements * 4, device.index)
+    samples = samples_buffer.tensor("int32").view(num_chunks, sample_elements)
+    h2d_bytes = sum(nbytes for placement in placements for (_, nbytes) in placement.values())
     d2h_bytes = num_chunks * sample_elements * 4
-    launches = [0]
+    size = g.size_type_by_index_size(4)
 
-    # The plan is built once (host side, untimed) with the library's host-resident scan executor (include/giddy_b200.h
-    # group 4: C++, behind the C ABI); a step replays it: every copy and every launch below is enqueued by the library.
-    scan = kernel._library.create_scan(num_streams)
-    for index, shard in enumerate(chunks):
-        chunk = scan.chunk(index)
-        runs, segments = shard.run_slice(), shard.segment_slice()
-        chunk.copy(dev["run_data"][runs], host["run_data"][runs])
-        chunk.copy(dev["run_lengths"][runs], host["run_lengths"][runs])
-        chunk.copy(dev["position_anchors"][segments], host["position_anchors"][segments])
-        chunk.copy(dev["intra_run_anchor_offsets"][segments], host["intra_run_anchor_offsets"][segments])
-        arguments = rle_arguments(
-            g, column, out.data_ptr() + 4 * shard.first_element, dev["position_anchors"].data_ptr() + 4 * shard.s0,
-            dev["intra_run_anchor_offsets"].data_ptr() + 2 * shard.s0, shard.s1 - shard.s0, shard.num_elements,
-            run_data=dev["run_data"], run_lengths=dev["run_lengths"])
-        config = kernel.resolve_launch_configuration({"length": g.size_t(shard.num_elements), "segment_length": g.size_t(L)})
-        scan.add_launch(index, kernel, config, arguments)
-        tail = shard.first_element + shard.num_elements - sample_elements
-        chunk.copy_back(samples[index], out[tail: tail + sample_elements])
+    def chunk_span(placement):
+        first = min(offset for (offset, _) in placement.values())
+        last = max(offset + nbytes for (offset, nbytes) in placement.values())
+        return first, last - first
 
-    def step():
-        scan.run()
-        launches[0] += num_chunks
+    def build(copy_back):
+        """copy_back: 'sample', 'all' or None (decode only); returns (scan, pinned host output or None)"""
+        scan = library.create_scan(num_streams)
+        host_out = library.host_alloc(n * 4, device.index) if copy_back == "all" else None
+        for index, (shard, placement) in enumerate(zip(shards, placements)):
+            first, span = chunk_span(placement)
+            scan.add_copy(index, dev_packed.data_ptr() + first, host_packed.address + first, span)  # ONE copy per chunk
+            base = dev_packed.data_ptr()
+            first_element, count = int(shard.first_element), int(shard.num_elements)
+            arguments = {
+                "decompressed": g.ptr(out.data_ptr() + 4 * first_element, "u32"),
+                "run_data": g.cptr(base + placement["run_data"][0], "u32"), "run_lengths": g.cptr(base + placement["run_lengths"][0], "u16"),
+                "position_anchors": g.cptr(base + placement["position_anchors"][0], "u32"),
+                "intra_run_anchor_offsets": g.cptr(base + placement["intra_run_anchor_offsets"][0], "u16"),
+                "segment_length": size(L), "num_segments": size(int(shard.num_segments)), "num_element_runs": size(int(shard.num_runs)),
+                "length": size(count)}
+            config = kernel.resolve_launch_configuration({"length": g.size_t(count), "segment_length": g.size_t(L)})
+            scan.add_launch(index, kernel, config, arguments)
+            if copy_back == "sample":
+                tail = first_element + count - sample_elements
+                scan.add_copy_back(index, samples[index], out[tail: tail + sample_elements])
+            elif copy_back == "all":
+                scan.add_copy_back(index, host_out.address + 4 * first_element, out.data_ptr() + 4 * first_element, 4 * count)
+        return scan, host_out
+
+    def copies_only(direction, host_out=None):
+        """The same transfers with nothing else: the ceiling the executor's overlap is measured against."""
+        scan = library.create_scan(num_streams)
+        for index, (shard, placement) in enumerate(zip(shards, placements)):
+            if direction == "h2d":
+                first, span = chunk_span(placement)
+                scan.add_copy(index, dev_packed.data_ptr() + first, host_packed.address + first, span)
+            else:
+                first_element, count = int(shard.first_element), int(shard.num_elements)
+                scan.add_copy_back(index, host_out.address + 4 * first_element, out.data_ptr() + 4 * first_element, 4 * count)
+        return scan
 
     def barrier():
         if distributed:
@@ -478,66 +569,80 @@ def run_e2e(args, torch, np, g, columns, kernel, column, out, device, distribute
             dist.barrier()
         torch.cuda.synchronize()
 
-    steps, warmup = max(3, min(args.steps, 20)), 3
+    def timed(scan, steps, warmup=3):
+        """ms per pass, max over ranks: CUDA events around `steps` replays between two barriers"""
+        for _ in range(warmup):
+            scan.run()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record()
+        for _ in range(steps):
+            scan.run()
+        end.record()
+        barrier()
+        elapsed_ms = start.elapsed_time(end)
+        if distributed:
+            import torch.distributed as dist
+            t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed_ms = float(t.item())
+        return elapsed_ms / steps
+
+    def gbs(nbytes, ms):
+        return nbytes / (ms / 1e3) / 1e9
+
+    steps = max(3, min(args.steps, 20))
+    resident = out[:n].clone()  # what the in-HBM decode of the timed region produced
     out.zero_()
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    # the sample read back must be what the in-HBM decode produced
-    reference_tail = chunks[-1].first_element + chunks[-1].num_elements - sample_elements
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    launches[0] = 0
-    start.record()
-    for _ in range(steps):
-        step()
-    end.record()
-    barrier()
-    elapsed_ms = start.elapsed_time(end)
-    if distributed:
-        import torch.distributed as dist
-        t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    ok = bool(torch.equal(samples[-1], out[reference_tail: reference_tail + sample_elements].cpu()))
-    result = {"value": world * n * 4 * steps / (elapsed_ms / 1e3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d_bytes,
-              "d2h_bytes_per_step": d2h_bytes, "steps": steps, "ms_per_step": elapsed_ms / steps, "gpu_launches": launches[0],
-              "chunks": num_chunks, "streams": num_streams, "sample_matches": ok,
-              "what": "pinned host compressed column -> H2D in %d segment-range chunks on %d streams -> decode per chunk -> "
-                      "D2H of each chunk's last %d elements; the decompressed column stays in HBM for its GPU consumer; "
-                      "planned once and replayed by the library's host-resident scan executor (giddy_scan_run)" % (
-                          num_chunks, num_streams, sample_elements),
-              "h2d_gbs": h2d_bytes * steps / (elapsed_ms / 1e3) / 1e9}
-    # variant: the same plan replayed as one captured CUDA graph
+    dev_packed.zero_()
+    scan, _ = build("sample")
+    ms = timed(scan, steps)
+    matches = bool(torch.equal(out[:n], resident))
+    last = shards[-1]
+    tail = int(last.first_element + last.num_elements) - sample_elements
+    sample_ok = bool(torch.equal(samples[-1], resident[tail: tail + sample_elements].cpu()))
+    ceiling_ms = timed(copies_only("h2d"), steps)
+    result = {"value": world * gbs(n * 4, ms), "unit": "GB/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": steps,
+              "ms_per_step": ms, "gpu_launches": num_chunks * steps, "chunks": num_chunks, "streams": num_streams, "copies_per_step": 2 * num_chunks,
+              "sample_matches": sample_ok, "matches_resident_decode": matches,
+              "what": "e2e.value: pinned host compressed column (chunk-major, giddy_host_alloc) -> ONE H2D copy per segment-range chunk (%d chunks on %d "
+                      "streams) -> decode per chunk -> D2H of each chunk's last %d elements; the decompressed column stays in HBM for its GPU "
+                      "consumer.  e2e.result_returning copies every chunk's whole output back instead.  Both replayed by the library's scan "
+                      "executor (giddy_scan_run)" % (num_chunks, num_streams, sample_elements),
+              "h2d_gbs_per_gpu": gbs(h2d_bytes, ms), "h2d_ceiling_gbs_per_gpu": gbs(h2d_bytes, ceiling_ms),
+              "h2d_frac_of_ceiling": ceiling_ms / ms,
+              "ceiling": "the same %d copies on the same streams with no kernels, all ranks at once" % num_chunks,
+              "host_memory": {"numa_node": host_packed.numa_node, "allocator": "giddy_host_alloc (mmap + mbind + cudaHostRegister)"}}
+    # the same plan replayed as one captured CUDA graph
     try:
         scan.set_graph_replay(True)
-        step()
-        torch.cuda.synchronize()
-        s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s1.record()
-        for _ in range(steps):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
-        result["with_graph_replay"] = {"value": world * n * 4 * steps / (s1.elapsed_time(e1) / 1e3) / 1e9, "unit": "GB/s", "steps": steps}
+        graph_ms = timed(scan, steps, warmup=2)
+        result["with_graph_replay"] = {"value": world * gbs(n * 4, graph_ms), "unit": "GB/s", "steps": steps}
     except Exception as error:
         result["with_graph_replay"] = {"skipped": str(error)[:100]}
-    scan.set_graph_replay(False)
-    # variant: also bring the whole decompressed column back to the host (PCIe-bound on the 4 GiB output)
+    del scan
+    # result-returning: every chunk's whole output goes back to pinned host memory, overlapped with the following chunks
     try:
-        host_out = torch.empty(n, dtype=torch.int32).pin_memory()
-        torch.cuda.synchronize()
-        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s2.record()
-        step()
-        host_out.copy_(out[:n], non_blocking=True)
-        e2.record()
-        torch.cuda.synchronize()
-        result["with_full_output_d2h"] = {"value": world * n * 4 / (s2.elapsed_time(e2) / 1e3) / 1e9, "unit": "GB/s",
-                                          "d2h_bytes_per_step": n * 4 + d2h_bytes, "steps": 1}
-        del host_out
-    except Exception as error:  # pinned allocation of 4 GiB may be refused on a small host
-        result["with_full_output_d2h"] = {"skipped": str(error)[:100]}
+        full_steps = max(5, min(args.steps, 10))
+        out.zero_()
+        scan, host_out = build("all")
+        full_ms = timed(scan, full_steps, warmup=2)
+        returned = host_out.tensor("int32")
+        ok = True
+        for shard in (shards[0], shards[num_chunks // 2], shards[-1]):
+            a, b = int(shard.first_element), int(shard.first_element + shard.num_elements)
+            ok = ok and bool(torch.equal(returned[a:b], resident[a:b].cpu()))
+        d2h_ceiling_ms = timed(copies_only("d2h", host_out), full_steps, warmup=1)
+        result["result_returning"] = {
+            "value": world * gbs(n * 4, full_ms), "unit": "GB/s", "steps": full_steps, "ms_per_step": full_ms, "h2d_bytes_per_step": h2d_bytes,
+            "d2h_bytes_per_step": n * 4, "returned_column_matches": ok, "d2h_gbs_per_gpu": gbs(n * 4, full_ms),
+            "d2h_ceiling_gbs_per_gpu": gbs(n * 4, d2h_ceiling_ms), "d2h_frac_of_ceiling": d2h_ceiling_ms / full_ms,
+            "what": "as e2e.value, but each chunk's whole decompressed output (256 MB) is copied back to pinned host memory on the chunk's "
+                    "stream while later chunks are copied in and decoded; bound by the D2H link: 10x more bytes go back than come in"}
+        del scan, host_out
+    except Exception as error:  # e.g. 4 GiB of pinned memory refused on a small host
+        result["result_returning"] = {"skipped": str(error)[:200]}
+    del resident
     return result
 
 

@@ -34,6 +34,13 @@ RANK = int(os.environ.get("RANK", "0"))
 LOCAL_RANK = int(os.environ.get("LOCAL_RANK", "0"))
 
 
+LOG_FILE = None  # where progress lines go (None: stdout); bench.py sends them to stderr -- its stdout carries one JSON line
+
+
+def log(text):
+    print(text, file=LOG_FILE or sys.stdout, flush=True)
+
+
 def generator(device, seed):
     gen = torch.Generator(device=device)
     gen.manual_seed(seed + 1000 * RANK)
@@ -69,10 +76,22 @@ def time_passes(run, repeats):
     return ms / 1e3
 
 
+def distinct_sorted_positions(device, gen, n, p):
+    """Exactly p distinct positions in [0, n), ascending: draw a few too many, drop duplicates, then drop a random surplus."""
+    if p == 0:
+        return torch.empty(0, dtype=torch.int64, device=device)
+    drawn = torch.unique(torch.randint(0, n, (p + p // 50 + 1024,), generator=gen, device=device, dtype=torch.int64))
+    while drawn.numel() < p:  # (only for tiny n)
+        drawn = torch.unique(torch.cat((drawn, torch.randint(0, n, (p,), generator=gen, device=device, dtype=torch.int64))))
+    keep = torch.randperm(drawn.numel(), generator=gen, device=device)[:p]
+    return drawn[torch.sort(keep).values]
+
+
 def report(rows, peak, config, chain, output_bytes, algorithmic_bytes, seconds, verified, reference_seconds=None, extra=None):
+    # (peak None: a row which is not bound by HBM -- the host-resident scan is bound by the host link -- has no HBM fraction)
     row = {"config": config, "chain": chain, "n_gpus": WORLD, "ms": seconds * 1e3,
            "decompressed_gbs": WORLD * output_bytes / seconds / 1e9, "algorithmic_gbs": WORLD * algorithmic_bytes / seconds / 1e9,
-           "frac_of_measured_peak_per_gpu": algorithmic_bytes / seconds / 1e9 / peak, "output_bytes_per_gpu": output_bytes,
+           "frac_of_measured_peak_per_gpu": (algorithmic_bytes / seconds / 1e9 / peak) if peak else None, "output_bytes_per_gpu": output_bytes,
            "algorithmic_bytes_per_gpu": algorithmic_bytes, "bit_exact": verified}
     if reference_seconds is not None:
         row.update({"reference_kernels_ms": reference_seconds * 1e3, "reference_kernels_decompressed_gbs": WORLD * output_bytes / reference_seconds / 1e9,
@@ -81,9 +100,9 @@ def report(rows, peak, config, chain, output_bytes, algorithmic_bytes, seconds, 
         row.update(extra)
     rows.append(row)
     if RANK == 0:
-        print("%-5s %-44s %9.3f ms  out %8.1f GB/s  alg %8.1f GB/s (%5.1f%% of %.0f per GPU)  exact=%s  ref %s" % (
-            config, chain, row["ms"], row["decompressed_gbs"], row["algorithmic_gbs"], 100 * row["frac_of_measured_peak_per_gpu"], peak, verified,
-            ("%.3f ms (x%.2f)" % (reference_seconds * 1e3, reference_seconds / seconds)) if reference_seconds else "-"), flush=True)
+        log("%-5s %-44s %9.3f ms  out %8.1f GB/s  alg %8.1f GB/s (%5.1f%% of %.0f per GPU)  exact=%s  ref %s" % (
+            config, chain, row["ms"], row["decompressed_gbs"], row["algorithmic_gbs"], 100 * (row["frac_of_measured_peak_per_gpu"] or 0), peak or 0, verified,
+            ("%.3f ms (x%.2f)" % (reference_seconds * 1e3, reference_seconds / seconds)) if reference_seconds else "-"))
 
 
 def with_reference(reference, run_with, repeats):
@@ -93,7 +112,7 @@ def with_reference(reference, run_with, repeats):
         return time_passes(lambda: run_with(reference), max(3, repeats // 4))
     except Exception as error:  # the reference is not defined on every shape
         if RANK == 0:
-            print("      (reference kernels failed: %s)" % str(error)[:120])
+            log("      (reference kernels failed: %s)" % str(error)[:120])
         return None
 
 
@@ -170,9 +189,8 @@ def cfg3(args, device, product, reference, rows, peak):
     columns_module = __import__("libgiddy_b200.columns", fromlist=["broadcast_dictionary"])
     columns_module.broadcast_dictionary(dictionary, 0)  # the one collective of the multi-GPU path (NCCL over NVLink)
     indices = torch.randint(0, 256, (n,), generator=gen, device=device, dtype=torch.int16).to(torch.uint8)
-    p = n // 100
-    positions = torch.unique(torch.randint(0, n, (p,), generator=gen, device=device, dtype=torch.int64))  # sorted, distinct
-    p = positions.numel()
+    p = n // 100  # exactly floor(0.01 n) distinct sorted positions (5 368 709 at full size)
+    positions = distinct_sorted_positions(device, gen, n, p)
     patches = torch.randint(-(1 << 62), 1 << 62, (p,), generator=gen, device=device, dtype=torch.int64) | 1
     positions32 = positions.to(torch.int32)
     out = torch.empty(n, dtype=torch.int64, device=device)
@@ -307,8 +325,7 @@ def cfg4(args, device, product, reference, rows, peak):
 
 def synthesize_ci_patches(device, gen, n, density, A, run_length):
     p = int(n * density)
-    positions = torch.unique(torch.randint(0, n, (p,), generator=gen, device=device, dtype=torch.int64))
-    p = positions.numel()
+    positions = distinct_sorted_positions(device, gen, n, p)
     values = torch.randint(-(1 << 31), 1 << 31, (p,), generator=gen, device=device, dtype=torch.int64).to(torch.int32)
     assert A % run_length == 0  # so that fixed-length runs never straddle an anchoring period
     num_runs = (p + run_length - 1) // run_length
@@ -568,15 +585,96 @@ def host_resident_scan(args, device, product, rows, n, L, A, K, S_, p, num_runs,
     raw_seconds = time_passes(raw_copy, repeats)
     extra.update({"uncompressed_copy_ms": raw_seconds * 1e3, "uncompressed_copy_gbs": WORLD * output_bytes / raw_seconds / 1e9,
                   "gain_over_uncompressed_copy": raw_seconds / seconds})
-    report(rows, 1.0, "cfg5", "host-resident scan: 3 columns, pinned H2D + decode overlap", output_bytes, h2d_bytes + output_bytes, seconds, verified,
+    report(rows, None, "cfg5", "host-resident scan: 3 columns, pinned H2D + decode overlap", output_bytes, h2d_bytes + output_bytes, seconds, verified,
            extra=extra)
     if RANK == 0:
-        print("      host-resident: %.1f GB/s decompressed over %d GPU(s) vs %.1f GB/s copying the uncompressed columns: gain x%.2f "
-              "(compression ratio %.2f, H2D %.1f GB/s per GPU)" % (WORLD * output_bytes / seconds / 1e9, WORLD, WORLD * output_bytes / raw_seconds / 1e9,
-                                                                raw_seconds / seconds, output_bytes / h2d_bytes, h2d_bytes / seconds / 1e9))
+        log("      host-resident: %.1f GB/s decompressed over %d GPU(s) vs %.1f GB/s copying the uncompressed columns: gain x%.2f "
+            "(compression ratio %.2f, H2D %.1f GB/s per GPU)" % (WORLD * output_bytes / seconds / 1e9, WORLD, WORLD * output_bytes / raw_seconds / 1e9,
+                                                              raw_seconds / seconds, output_bytes / h2d_bytes, h2d_bytes / seconds / 1e9))
 
 
-CONFIGS = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}
+# ---------------------------------------------------------------------------------------------------------------
+# strong scaling: ONE column of cfg2's shape cut into contiguous segment ranges, one per GPU, by the library's C++ planner
+# ---------------------------------------------------------------------------------------------------------------
+
+def strong(args, device, product, reference, rows, peak):
+    """The same 2^30-element RLE column on every rank (rank-independent seed); rank r decodes segments [s0, s1) of it as a
+    self-contained column: its runs, its segments' anchors with the first run's index subtracted (giddy_shard_plan says
+    which and by how much).  Total work is fixed as the number of GPUs grows; time is the max over ranks."""
+    import numpy as np
+    from libgiddy_b200 import _native as N
+    from libgiddy_b200 import columns
+    n, L = (1 << 30) >> args.shrink, 1024
+    gen = torch.Generator(device=device)
+    gen.manual_seed(3)
+    values, lengths64, starts, anchors, intra, R = synthesize_runs(device, gen, n, 31, L, torch.int16)
+    lengths = lengths64.to(torch.int16)
+    num_segments = (n + L - 1) // L
+    host_anchors = anchors.cpu().numpy().view(np.uint32)  # planning reads a host copy of the anchors: 4 bytes per segment
+    layout = columns._layout(N.SCHEME_RUN_LENGTH_ENCODING, n, L, index_size=4, uncompressed_size=4, compressed_size=2, num_runs=R, anchors=host_anchors)
+    s0, s1 = product.split_segments(num_segments, WORLD, RANK)
+    shard = product.shard_plan(layout, s0, s1)
+    runs, rebase = shard.slice("run_data"), shard.slice("position_anchors").rebase
+    # the shard as a column of its own, in buffers of its own (on one box the slices are cut on the device; across boxes
+    # they would be copied out of the host-resident column with giddy_slice_copy)
+    shard_values = values[runs.first: runs.first + runs.count].clone()
+    shard_lengths = lengths[runs.first: runs.first + runs.count].clone()
+    shard_anchors = (anchors[s0:s1].to(torch.int64) - rebase).to(torch.int32)
+    shard_intra = intra[s0:s1].clone()
+    count = int(shard.num_elements)
+    expected = torch.repeat_interleave(values, lengths64)[shard.first_element: shard.first_element + count].clone()
+    del values, lengths, lengths64, starts, anchors, intra
+    torch.cuda.empty_cache()
+    out = torch.empty(count + 64, dtype=torch.int32, device=device)
+
+    def run(library=product):
+        S.run_length_encoding(out, shard_values, shard_lengths, shard_anchors, shard_intra, L, s1 - s0, int(shard.num_runs), count,
+                              uncompressed_size=4, run_length_size=2, library=library)
+    run()
+    verified = bool(torch.equal(out[:count], expected))
+    del expected
+    if WORLD > 1:
+        ok = torch.tensor([1 if verified else 0], device=device)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        verified = bool(ok.item())
+    seconds = time_passes(run, args.repeats)
+    shard_bytes = nbytes(shard_values, shard_lengths, shard_anchors, shard_intra) + count * 4
+    # (report() multiplies per-GPU bytes by the world size: pass the per-GPU share of the one column)
+    report(rows, peak, "strong", "ONE RLE column (n=2^%d) split into %d segment-range shards" % (30 - args.shrink, WORLD), n * 4 // WORLD, shard_bytes, seconds, verified,
+           extra={"scaling": "strong", "whole_column_decompressed_gbs": n * 4 / seconds / 1e9, "segments_per_shard": s1 - s0, "planner": "giddy_shard_plan"})
+
+
+CONFIGS = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "strong": strong}
+
+
+class Options:
+    """The knobs of a run (the command line's, or a caller's: bench.py, tests/test_baseline_sizes.py)."""
+
+    def __init__(self, shrink=0, repeats=20, chunks=16, streams=4, graph_replay=False, cfg4_columns=8, sweep_grids=False):
+        self.shrink, self.repeats, self.chunks, self.streams = shrink, repeats, chunks, streams
+        self.graph_replay, self.cfg4_columns, self.sweep_grids = graph_replay, cfg4_columns, sweep_grids
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def run_configs(names, options, device, product=None, reference=None):
+    """Run the named configurations on the current device (all ranks of a torchrun job must call this together) and
+    return their rows."""
+    product = product or g.default_library()
+    peak, rows = measured_peak(), []
+    for name in names:
+        t0 = time.time()
+        CONFIGS[name](options, device, product, reference, rows, peak)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        if RANK == 0:
+            log("      [%s took %.1f s]" % (name, time.time() - t0))
+    return rows
 
 
 def main():
@@ -590,38 +688,29 @@ def main():
     parser.add_argument("--cfg4-columns", type=int, default=8, help="columns of cfg4 spread over the ranks (1 per GPU at 8 GPUs)")
     parser.add_argument("--no-reference", action="store_true")
     parser.add_argument("--sweep-grids", action="store_true", help="also time the fused patched decoders under several grid sizes")
+    parser.add_argument("--library", default="", help="path of another build of the product library (make variant ...)")
     parser.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.json"))
     args = parser.parse_args()
 
     torch.cuda.set_device(LOCAL_RANK)
     device = torch.device("cuda", LOCAL_RANK)
     if WORLD > 1:
-        from libgiddy_b200 import hostmem
-        hostmem.bind_to_numa_node_of_gpu(LOCAL_RANK)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=device)
-    product = g.default_library()
+    product = g.Library(args.library) if args.library else g.default_library()
+    if WORLD > 1:
+        product.host_bind_thread_to_device(LOCAL_RANK)
     reference_path = os.path.join(ROOT, "oracle", "_ref", "libgiddy_ref.so")
     reference = g.Library(reference_path) if os.path.exists(reference_path) and not args.no_reference else None
-    try:
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-    except Exception:
-        peak = 6650.0
     only = [s for s in args.only.split(",") if s]
-    rows = []
-    for name, function in CONFIGS.items():
-        if only and name not in only:
-            continue
-        t0 = time.time()
-        function(args, device, product, reference, rows, peak)
-        torch.cuda.synchronize()
-        torch.cuda.empty_cache()
-        if RANK == 0:
-            print("      [%s took %.1f s]" % (name, time.time() - t0), flush=True)
+    names = [name for name in CONFIGS if (name in only if only else name != "strong" or WORLD > 1)]
+    options = Options(args.shrink, args.repeats, args.chunks, args.streams, args.graph_replay, args.cfg4_columns, args.sweep_grids)
+    rows = run_configs(names, options, device, product, reference)
     if RANK == 0:
         os.makedirs(os.path.dirname(args.out), exist_ok=True)
         with open(args.out, "w") as f:
-            json.dump({"device": torch.cuda.get_device_name(device), "n_gpus": WORLD, "peak_gbs": peak, "shrink": args.shrink, "rows": rows}, f, indent=1)
+            json.dump({"device": torch.cuda.get_device_name(device), "n_gpus": WORLD, "peak_gbs": measured_peak(), "shrink": args.shrink,
+                       "library": product.path, "rows": rows}, f, indent=1)
     if WORLD > 1:
         torch.distributed.destroy_process_group()
 

@@ -26,6 +26,22 @@ def lib():
     return _lib
 
 
+def use_native_build():
+    """For the timed CPU baseline: rebuild the oracle -march=native ON THIS MACHINE (the committed recipe builds it
+    -march=x86-64-v3 so that the binary runs on any box it travels to) and switch to it.  Returns the -march used;
+    without a compiler here the portable build stays in use."""
+    global _lib
+    import subprocess
+    native = os.path.join(_HERE, "libgiddy_oracle_native.so")
+    try:
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", native,
+                        os.path.join(_HERE, "giddy_oracle.cpp")], check=True, capture_output=True, timeout=300)
+        _lib = ctypes.CDLL(native)
+        return "native"
+    except Exception:
+        return "x86-64-v3"
+
+
 def num_threads():
     return lib().giddy_oracle_num_threads()
 

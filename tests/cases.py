@@ -513,6 +513,15 @@ def all_cases():
     cases.append(patched_dictionary_case(6, 50000, 2, 2, 5000, 50000))                   # every element patched
     cases.append(patched_dictionary_case(7, 9, 8, 1, 3, 2))
     cases.append(patched_dictionary_case(8, 1 << 22, 4, 1, 256, 200000))
+    # cached dictionaries between 15 and 48 KiB: the kernel's own static shared memory plus the dictionary exceed the 48 KiB a
+    # kernel gets without opting in (the launcher must opt in on the sum, not on the dynamic part alone)
+    cases.append(patched_dictionary_case(9, 1 << 18, 8, 2, 4096, 3000, cache=True))       # 32 KiB
+    cases.append(patched_dictionary_case(10, 1 << 18, 4, 2, 6000, 3000, cache=True))      # 23.4 KiB
+    cases.append(patched_dictionary_case(11, 1 << 18, 8, 2, 5800, 3000, cache=True))      # 45.3 KiB
+    # many patches per tile: several patches in one 16-byte vector, more than 32 (and more than 255) patches in a tile
+    cases.append(patched_dictionary_case(12, 1 << 16, 1, 1, 256, 20000))                  # U = 1: 4096-element tiles, ~1250 patches each
+    cases.append(patched_dictionary_case(13, 1 << 17, 2, 1, 256, 30000))
+    cases.append(patched_dictionary_case(14, 1 << 18, 8, 1, 256, 100000))                 # 38 % of the elements patched
     # Extension: Frame of Reference + compressed-indices patches, fused (7 keys)
     for (I, U, C, model, MI) in [(4, 2, 1, "linear", 4), (4, 4, 1, "linear", 4), (4, 4, 2, "linear", 4), (8, 4, 2, "linear", 8),
                                  (4, 2, 1, "constant", 4), (4, 4, 1, "constant", 4), (4, 4, 2, "constant", 4)]:
@@ -525,6 +534,8 @@ def all_cases():
     cases.append(patched_for_case(6, 60000, 1024, 2, 1, "constant", 60000, 1024, max_run_length=1))  # every element patched, one-patch runs
     cases.append(patched_for_case(7, 1 << 22, 4096, 4, 2, "constant", 150000, 100000, max_run_length=500))  # long anchoring period
     cases.append(patched_for_case(8, 1 << 21, 1024, 4, 2, "linear", 30000, 16, max_run_length=16))   # tiny anchoring period
+    cases.append(patched_for_case(9, 1 << 18, 1024, 2, 1, "linear", 60000, 1024))                    # U = 2: ~470 patches per 2048-element tile
+    cases.append(patched_for_case(10, 1 << 18, 1024, 4, 2, "constant", 80000, 512, max_run_length=32))
     # Incidence bitmaps (5 keys)
     for (U, use_dictionary) in [(1, True), (2, True), (4, True), (8, True), (1, False)]:
         cases.append(bitmaps_case(0, 64 * 1024, U, 16, use_dictionary))

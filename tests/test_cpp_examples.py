@@ -24,3 +24,15 @@ def test_three_modes_of_use_reproduce_the_known_answer(library):
     result = subprocess.run([BINARY], capture_output=True, text=True)
     assert result.returncode == 0, result.stdout + result.stderr
     assert result.stdout.count("SUCCESS") == 3, result.stdout
+
+
+@pytest.mark.gpu
+def test_sharded_scan_over_all_visible_gpus(library):
+    """examples/sharded_scan.cpp: one column cut into segment-range shards by the library's planner, one per GPU (worker
+    threads of a device group), the fused decoder and the two-kernel chain on every shard, a dictionary broadcast."""
+    binary = os.path.join(ROOT, "examples", "bin", "sharded_scan")
+    if not os.path.exists(binary):
+        subprocess.run(["make", "-C", ROOT, "examples"], check=True, capture_output=True)
+    result = subprocess.run([binary, "22"], capture_output=True, text=True, timeout=600)
+    assert result.returncode == 0, result.stdout + result.stderr
+    assert result.stdout.count("SUCCESS") == 3, result.stdout
