@@ -38,10 +38,16 @@ ORACLE_MARCH ?= x86-64-v3
 
 .PHONY: all lib oracle ref examples sass clean variant
 
-# A build of the whole library under other compile-time settings, for A/B measurements on the GPU box:
-#   make variant NAME=patched5 DEFS="-DGIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR=5"   -> benchmarks/variants/patched5/libgiddy_b200.so
-# (benchmarks load it with libgiddy_b200.Library(path); the .so is git-ignored but travels to the box)
-variant:
+# A build of the library under other compile-time settings, for A/B measurements on the GPU box:
+#   make variant NAME=p5 DEFS="-DGIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR=5" REBUILD="abi/abi_patched host/registration"
+#     -> benchmarks/variants/p5/libgiddy_b200.so
+# Starts from the default build's objects and recompiles only the translation units named in REBUILD (those the settings
+# touch; default: all).  Benchmarks load it with libgiddy_b200.Library(path); the .so is git-ignored but travels to the box.
+REBUILD ?= $(patsubst $(BUILD_DIR)/%.o,%,$(ABI_OBJS) $(HOST_OBJS))
+variant: lib
+	@mkdir -p build/variants/$(NAME)/obj
+	cp -r $(BUILD_DIR)/abi $(BUILD_DIR)/host build/variants/$(NAME)/obj/
+	rm -f $(foreach unit,$(REBUILD),build/variants/$(NAME)/obj/$(unit).o)
 	$(MAKE) -j8 lib BUILD_DIR=build/variants/$(NAME)/obj LIB_DIR=benchmarks/variants/$(NAME) EXTRA_DEFS="$(DEFS)"
 
 all: lib oracle

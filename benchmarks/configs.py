@@ -222,7 +222,8 @@ def cfg3(args, device, product, reference, rows, peak):
 
     # extension: the same column decoded and patched in one pass
     def fused(limits=None):
-        S.patched_dictionary(out, indices, dictionary, n, 256, patches, positions32, p, uncompressed_size=8, dictionary_index_size=1, limits=limits)
+        S.patched_dictionary(out, indices, dictionary, n, 256, patches, positions32, p, uncompressed_size=8, dictionary_index_size=1, limits=limits,
+                             library=product)
     out.zero_()
     fused()
     expected = dictionary[indices.to(torch.int64)]
@@ -393,7 +394,7 @@ def cfg5(args, device, product, reference, rows, peak):
     def fused_a(limits=None):
         S.patched_frame_of_reference(out_a, offsets, coefficients, n, L, patch_values, ci["run_lengths"], ci["offset_sizes"], ci["baselines"],
                                      ci["offsets_start"], ci["offset_bytes"], ci["anchors"], A, num_runs, p,
-                                     uncompressed_size=4, compressed_size=2, model="linear", limits=limits)
+                                     uncompressed_size=4, compressed_size=2, model="linear", limits=limits, library=product)
     out_a.zero_()
     fused_a()
     x = torch.arange(L, device=device, dtype=torch.int32).repeat(S_)

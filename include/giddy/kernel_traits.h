@@ -62,7 +62,9 @@
 /* Patched decoders (decode + patches in one pass): warp tiles of 32 x this many output vectors go grid-stride to the
  * warps of this many CTAs (of GIDDY_ELEMENTWISE_BLOCK_THREADS threads) per multiprocessor; an index of one patch range per
  * tile is built into a workspace before the decode. */
-#define GIDDY_PATCHED_UNROLL 8
+#ifndef GIDDY_PATCHED_UNROLL
+#define GIDDY_PATCHED_UNROLL 2
+#endif
 #ifndef GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR
 #define GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR 4
 #endif

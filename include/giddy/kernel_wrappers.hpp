@@ -949,7 +949,7 @@ namespace detail_patched {
 /// up to that size.
 inline void configure(launch_config_resolution_params_t& p, ::std::size_t length_in_elements, unsigned uncompressed_size)
 {
-	const ::std::size_t elements_per_block_tile = (::std::size_t) GIDDY_ELEMENTWISE_BLOCK_THREADS * GIDDY_PATCHED_UNROLL * (16 / uncompressed_size);
+	const ::std::size_t elements_per_block_tile = (::std::size_t) GIDDY_ELEMENTWISE_BLOCK_THREADS * GIDDY_PATCHED_UNROLL * (32 / uncompressed_size);
 	p.grid_construction_resolution  = launch_config_resolution_params_t::block;
 	p.serialization_option          = launch_config_resolution_params_t::auto_maximized;
 	p.length                        = util::div_rounding_up(length_in_elements, elements_per_block_tile);

@@ -24,7 +24,7 @@
  *      cites the reference __global__ function it replaces.
  *
  *  (3) Fused composite decoders, (4) host-resident scans, (5) shard planning, (6) host memory placement,
- *      (7) device groups: see the section comments below.
+ *      (7) device groups, (8) compressors: see the section comments below.
  *
  * Conventions: every function returns a giddy_status_t (0 = success) unless it
  * returns a pointer/count; on failure giddy_last_error() holds a message for the
@@ -578,6 +578,90 @@ GIDDY_API giddy_status_t giddy_device_group_broadcast(giddy_device_group_t* grou
 /* The same over a communicator of the caller's (one rank per process, e.g. under MPI): ncclBroadcast(buffer, buffer, bytes,
  * ncclUint8, root, comm, stream). */
 GIDDY_API giddy_status_t giddy_broadcast_dictionary(void* nccl_communicator, void* buffer, size_t bytes, int root, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* (8) Compressors.  The reference ships decompressors only ("compression ...  */
+/* is not included", README.md:128-130; its open Issue #3); these are their    */
+/* inverses, on the GPU, emitting exactly the layouts the decompressors of     */
+/* groups (1)-(3) read, anchor arrays included.  Registry keys: the            */
+/* decompressor's with "decompression::" replaced by "compression::".          */
+/* Every launcher takes an optional `status_flags` device word which has bits  */
+/* OR-ed into it when the column does not fit the format (it is never cleared: */
+/* zero it beforehand); the outputs are then unspecified but in bounds.        */
+/* ------------------------------------------------------------------------- */
+
+#define GIDDY_COMPRESSION_UNREPRESENTABLE 1u  /* an element does not fit: delta / offset too wide, value not in the dictionary, size field too narrow */
+#define GIDDY_COMPRESSION_CAPACITY        2u  /* more runs / bytes than the caller's arrays hold (the true count is still reported) */
+#define GIDDY_COMPRESSION_INDEX_OVERFLOW  4u  /* an anchor (run index, byte offset) does not fit its index type */
+
+/* format: delta::decompress, src/kernels/decompression/delta.cuh:66-108.  compressed[i] = x[i] - x[i-1] mod 2^(8U), x[-1] = base_value;
+ * anchor_values[s] = x[s * segment_length - 1] (base_value for s = 0). */
+GIDDY_API const void* giddy_b200_delta_compress_kernel(unsigned index_size, unsigned uncompressed_size, unsigned compressed_size);
+GIDDY_API giddy_status_t giddy_b200_delta_compress_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned index_size, unsigned uncompressed_size, unsigned compressed_size,
+	void* compressed, void* anchor_values, const void* uncompressed, uint64_t length, uint64_t segment_length, uint64_t base_value,
+	unsigned* status_flags);
+
+/* format: discard_zero_bytes::fixed_width::decompress, discard_zero_bytes_fixed.cuh:108-124.  compressed[i] = the low bytes of x[i]. */
+GIDDY_API const void* giddy_b200_discard_zero_bytes_fixed_compress_kernel(unsigned index_size, unsigned uncompressed_size, unsigned compressed_size);
+GIDDY_API giddy_status_t giddy_b200_discard_zero_bytes_fixed_compress_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned index_size, unsigned uncompressed_size, unsigned compressed_size,
+	void* compressed, const void* uncompressed, uint64_t length, unsigned* status_flags);
+
+/* format: dictionary::decompress, dictionary.cuh:61-79.  compressed[i] = index of x[i] in dictionary_entries, which must ascend. */
+GIDDY_API const void* giddy_b200_dictionary_compress_kernel(unsigned index_size, unsigned uncompressed_size, unsigned dictionary_index_size);
+GIDDY_API giddy_status_t giddy_b200_dictionary_compress_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned index_size, unsigned uncompressed_size, unsigned dictionary_index_size,
+	void* compressed, const void* uncompressed, const void* dictionary_entries, uint64_t num_dictionary_entries, uint64_t length,
+	unsigned* status_flags);
+
+/* format: frame_of_reference::decompress, frame_of_reference.cuh:35-80.  Per segment, constant: c0 = min + 2^(8C-1); linear: c1 =
+ * round-half-even((last - first) / (L - 1)), c0 = first + min residual + 2^(8C-1); compressed[i] = x[i] - model(i - s * L).
+ * Values are signed; coefficients int32 (1 or 2 per segment). */
+GIDDY_API const void* giddy_b200_frame_of_reference_compress_kernel(unsigned index_size, unsigned uncompressed_size, unsigned compressed_size, giddy_model_t model);
+GIDDY_API giddy_status_t giddy_b200_frame_of_reference_compress_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned index_size, unsigned uncompressed_size, unsigned compressed_size, giddy_model_t model,
+	void* compressed, void* segment_model_coefficients, const void* uncompressed, uint64_t length, uint64_t segment_length,
+	unsigned* status_flags);
+
+/* format: run_length_encoding::decompress, run_length_encoding.cuh:284-374.  Runs of equal adjacent elements, cut every
+ * max_run_length elements (0: the run-length type's maximum).  run_data / run_lengths hold run_capacity entries;
+ * *num_element_runs (device, size_type<run_index_size>, optional) receives the number of runs. */
+GIDDY_API const void* giddy_b200_run_length_encoding_compress_kernel(unsigned uncompressed_index_size, unsigned uncompressed_size, unsigned run_length_size, unsigned run_index_size);
+GIDDY_API giddy_status_t giddy_b200_run_length_encoding_compress_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned uncompressed_index_size, unsigned uncompressed_size, unsigned run_length_size, unsigned run_index_size,
+	void* run_data, void* run_lengths, void* position_anchors, void* intra_run_anchor_offsets, void* num_element_runs,
+	const void* uncompressed, uint64_t length, uint64_t segment_length, uint64_t max_run_length, uint64_t run_capacity,
+	unsigned* status_flags);
+
+/* format: run_position_encoding::decompress, run_position_encoding.cuh:122-359.  run_start_positions are absolute, or relative to
+ * the segment in which the run begins; max_run_length 0: runs are never cut. */
+GIDDY_API const void* giddy_b200_run_position_encoding_compress_kernel(unsigned uncompressed_index_size, unsigned uncompressed_size, unsigned position_offset_size, unsigned run_index_size);
+GIDDY_API giddy_status_t giddy_b200_run_position_encoding_compress_launch(
+	void* stream, const giddy_launch_config_t* config,
+	unsigned uncompressed_index_size, unsigned uncompressed_size, unsigned position_offset_size, int positions_are_relative, unsigned run_index_size,
+	void* run_data, void* run_start_positions, void* position_anchors, void* num_element_runs,
+	const void* uncompressed, uint64_t length, uint64_t segment_length, uint64_t max_run_length, uint64_t run_capacity,
+	unsigned* status_flags);
+
+/* format: discard_zero_bytes::variable_width::decompress, discard_zero_bytes_variable.cuh:335-439.  Element i takes
+ * max(significant bytes, min_represented_element_size) bytes of compressed_data (capacity data_capacity bytes); the size fields
+ * go into containers of element_sizes_container_size bytes; *num_bytes (device, uint64, optional) receives the stream's length. */
+GIDDY_API const void* giddy_b200_discard_zero_bytes_variable_compress_kernel(unsigned index_size, unsigned uncompressed_size, unsigned element_sizes_container_size);
+GIDDY_API giddy_status_t giddy_b200_discard_zero_bytes_variable_compress_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned index_size, unsigned uncompressed_size, unsigned element_sizes_container_size,
+	void* compressed_data, void* packed_element_sizes, void* position_anchors, void* num_bytes,
+	const void* uncompressed, uint64_t length, uint64_t segment_length, unsigned min_represented_element_size, unsigned bits_per_element_size,
+	uint64_t data_capacity, unsigned* status_flags);
+
+/* format: incidence_bitmaps::decompress, incidence_bitmaps.cuh:69-131.  Bit (i mod 32) of word i / 32 of bitmap b is set iff
+ * x[i] == dictionary_entries[b] (use_dictionary) or x[i] == b; bitmaps are round_up(ceil(length / 32), alignment) words apart. */
+GIDDY_API const void* giddy_b200_incidence_bitmaps_compress_kernel(unsigned uncompressed_size, int use_dictionary);
+GIDDY_API giddy_status_t giddy_b200_incidence_bitmaps_compress_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned uncompressed_size, unsigned bitmap_alignment_in_ints, int use_dictionary,
+	void* bitmaps, const void* uncompressed, const void* dictionary_entries, uint64_t length, unsigned num_bitmaps,
+	unsigned* status_flags);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -19,9 +19,10 @@ struct dict_entry_t { unsigned I, U, DI; const void* kernel; dict_launcher_t lau
 template <unsigned U>
 unsigned log2_tile_elements(const void* decompressed, const void* compressed_input, unsigned compressed_element_size)
 {
-	constexpr unsigned E = 16 / U;
-	const bool vectorizable = reinterpret_cast<uintptr_t>(decompressed) % 16 == 0 &&
-		reinterpret_cast<uintptr_t>(compressed_input) % (E * compressed_element_size) == 0;
+	constexpr unsigned E = 32 / U; // elements per 32-byte piece (kernels/patched.cuh)
+	const unsigned in_bytes = E * compressed_element_size;
+	const bool vectorizable = reinterpret_cast<uintptr_t>(decompressed) % 32 == 0 &&
+		reinterpret_cast<uintptr_t>(compressed_input) % (in_bytes < 16 ? in_bytes : 16) == 0;
 	unsigned elements = 32 * GIDDY_PATCHED_UNROLL * (vectorizable ? E : 1), log2 = 0;
 	while ((1u << log2) < elements) { log2++; }
 	return log2;
@@ -33,11 +34,11 @@ size_t tile_index_bytes(uint64_t num_tiles) { return (size_t) num_tiles * sizeof
 template <unsigned I>
 giddy_status_t build_tile_index(cudaStream_t stream, void* ranges, const void* positions, uint64_t num_patches, unsigned log2_tile, uint64_t num_tiles, uint64_t length)
 {
-	cudaError_t error = cudaMemsetAsync(ranges, 0, tile_index_bytes<I>(num_tiles), stream);
-	if (error != cudaSuccess) { return fail_cuda(error, "cudaMemsetAsync (patch tile index)"); }
+	// (the caller has filled the index with ones: tiles without patches read first == past_last)
 	if (num_patches == 0) { return GIDDY_SUCCESS; }
 	const unsigned threads = 256;
-	const uint64_t blocks = (num_patches + threads - 1) / threads;
+	const uint64_t blocks = (num_patches + 4 * threads - 1) / (4 * threads); // 4 patches per thread
+	cudaError_t error;
 	kernels::patched_detail::patch_tile_ranges<I><<<(unsigned) (blocks < 0x7fffffffull ? blocks : 0x7fffffffull), threads, 0, stream>>>(
 		static_cast<kernels::patched_detail::patch_range_t<I>*>(ranges), static_cast<const uint_t<I>*>(positions), (size_type<I>) num_patches, log2_tile, length);
 	error = cudaGetLastError();
@@ -55,6 +56,8 @@ giddy_status_t dict_launch(void* stream, const giddy_launch_config_t* cfg, void*
 	void* offsets = nullptr;
 	cudaError_t error = allocate_workspace(&offsets, tile_index_bytes<I>(num_tiles) + 16, s);
 	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocFromPoolAsync (patch tile index)"); }
+	error = cudaMemsetAsync(offsets, 0xff, tile_index_bytes<I>(num_tiles), s);
+	if (error != cudaSuccess) { cudaFreeAsync(offsets, s); return fail_cuda(error, "cudaMemsetAsync (patch tile index)"); }
 	giddy_status_t status = build_tile_index<I>(s, offsets, patch_indices, num_patches, log2_tile, num_tiles, n);
 	if (status == GIDDY_SUCCESS) {
 		status = launch(kernels::patched_dictionary_decompress<I, U, DI>, stream, cfg,
@@ -101,19 +104,17 @@ giddy_status_t for_launch(void* stream, const giddy_launch_config_t* cfg, void* 
 	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocFromPoolAsync (patch positions and tile index)"); }
 	void* positions = static_cast<unsigned char*>(workspace) + offsets_bytes;
 	giddy_status_t status = GIDDY_SUCCESS;
+	// one fill for both: index entries of all ones are empty ranges, and positions of all ones lie beyond any column (runs
+	// which cover fewer than data_length patches leave the rest of the list never applied, as the reference's kernel would)
+	error = cudaMemsetAsync(workspace, 0xff, offsets_bytes + data_length * I, s);
+	if (error != cudaSuccess) { cudaFreeAsync(workspace, s); return fail_cuda(error, "cudaMemsetAsync (patch positions and tile index)"); }
 	if (data_length != 0) {
-		// (runs which cover fewer than data_length patches leave the rest of the list at positions beyond any column:
-		// never applied -- the reference's kernel would skip them too)
-		error = cudaMemsetAsync(positions, 0xff, data_length * I, s);
-		if (error != cudaSuccess) { cudaFreeAsync(workspace, s); return fail_cuda(error, "cudaMemsetAsync (patch positions)"); }
 		const uint64_t periods = (data_length + anchoring_period - 1) / anchoring_period;
-		const unsigned warps_per_block = GIDDY_CI_SCATTER_WARPS_PER_BLOCK;
-		const uint64_t blocks = (periods + warps_per_block - 1) / warps_per_block;
-		kernels::expand_compressed_indices<I, II, II><<<(unsigned) (blocks < 0x7fffffffull ? blocks : 0x7fffffffull), warps_per_block * 32, 0, s>>>(
+		kernels::patched_detail::expand_compressed_indices_by_block<I, II, II><<<(unsigned) (periods < 0x7fffffffull ? periods : 0x7fffffffull), 64, 0, s>>>(
 			static_cast<uint_t<I>*>(positions), static_cast<const uint_t<II>*>(run_lengths), static_cast<const unsigned char*>(offset_sizes),
 			static_cast<const uint_t<I>*>(baselines), static_cast<const uint_t<II>*>(offsets_start),
 			static_cast<const unsigned char*>(offset_bytes), static_cast<const uint_t<II>*>(anchors),
-			(uint_t<II>) anchoring_period, (uint_t<II>) num_runs, (size_type<II>) data_length);
+			anchoring_period, num_runs, data_length);
 		error = cudaGetLastError();
 		if (error != cudaSuccess) { status = fail_cuda(error, "kernel launch (patch position decode)"); }
 	}

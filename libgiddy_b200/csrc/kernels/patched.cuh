@@ -15,7 +15,7 @@
 // Requirement (the only one beyond the two schemes' own): patch positions are in ASCENDING order, as a
 // compressor which emits exceptions while scanning the column produces them.
 //
-// Decomposition: the output is cut into warp tiles of 32 x GIDDY_PATCHED_UNROLL vectors, handed grid-stride to the
+// Decomposition: the output is cut into warp tiles of 32 x GIDDY_PATCHED_UNROLL 32-byte pieces, handed grid-stride to the
 // warps of a grid of GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR CTAs per multiprocessor.  What a warp needs to know is
 // which patches fall into its tile; that comes from a small index built just before, in stream order, into a
 // workspace the launcher takes from the library's pool for the duration of the call:
@@ -52,35 +52,33 @@ constexpr unsigned blocks_per_multiprocessor(unsigned index_size, unsigned eleme
 }
 
 // ---- decoders ----------------------------------------------------------------------------------------
-// load(v): the compressed bytes of output vector v; decode(pack, v): its 16 decoded bytes;
-// decode_one(i): element i on its own.  Same arithmetic as the stand-alone kernels in elementwise.cuh.
+// A lane's unit of work is a PIECE: 32 consecutive output bytes (E = 32 / U elements), decoded from E consecutive
+// compressed elements and stored with one 256-bit access -- the patched decoders are bound by instruction issue, not by
+// bytes, so every load, store and address computation should move as many bytes as the hardware lets it.
+// load(p): the compressed bytes of piece p; decode(pack, p): its 32 decoded bytes; decode_one(i): element i on its own.
+// Same arithmetic as the stand-alone kernels in elementwise.cuh.
 
-template <unsigned IndexSize, unsigned U, unsigned DI>
+constexpr unsigned piece_bytes = 32;
+
+__device__ __forceinline__ void store_piece(void* p, const byte_pack<piece_bytes>& v)
+{
+	store_streaming_32(p, v.u32);
+}
+
+template <unsigned IndexSize, unsigned U, unsigned DI, bool Cached>
 struct dictionary_decoder {
-	static constexpr unsigned E = 16 / U;
+	static constexpr unsigned E = piece_bytes / U;
 	static constexpr unsigned in_bytes = E * DI;
 	uint_t<U>*         __restrict__ decompressed;
 	const uint_t<DI>*  __restrict__ compressed_input;
-	const uint_t<U>*   __restrict__ table;     // global or shared
-	bool                            table_in_shared_memory;
+	const uint_t<U>*   __restrict__ table;     // shared memory if Cached, else global
 
-	__device__ __forceinline__ void setup(const uint_t<U>* __restrict__ dictionary_entries, uint64_t num_entries, bool cache)
+	__device__ __forceinline__ bool vectorizable() const { return is_aligned_to(decompressed, piece_bytes) && is_aligned_to(compressed_input, in_bytes < 16 ? in_bytes : 16); }
+	__device__ __forceinline__ uint_t<U> lookup(uint_t<DI> index) const { return Cached ? table[index] : __ldg(table + index); }
+	__device__ __forceinline__ byte_pack<in_bytes> load(uint64_t p) const { return load_pack<in_bytes>(compressed_input + p * E); }
+	__device__ __forceinline__ byte_pack<piece_bytes> decode(const byte_pack<in_bytes>& in, uint64_t) const
 	{
-		table = dictionary_entries;
-		table_in_shared_memory = cache;
-		if (cache) {
-			auto cached = reinterpret_cast<uint_t<U>*>(dynamic_shared_memory);
-			for (uint64_t i = threadIdx.x; i < num_entries; i += blockDim.x) { cached[i] = __ldg(dictionary_entries + i); }
-			__syncthreads();
-			table = cached;
-		}
-	}
-	__device__ __forceinline__ bool vectorizable() const { return is_aligned_to(decompressed, 16) && is_aligned_to(compressed_input, in_bytes); }
-	__device__ __forceinline__ uint_t<U> lookup(uint_t<DI> index) const { return table_in_shared_memory ? table[index] : __ldg(table + index); }
-	__device__ __forceinline__ byte_pack<in_bytes> load(uint64_t v) const { return load_pack<in_bytes>(compressed_input + v * E); }
-	__device__ __forceinline__ byte_pack<16> decode(const byte_pack<in_bytes>& in, uint64_t) const
-	{
-		byte_pack<16> out;
+		byte_pack<piece_bytes> out;
 		#pragma unroll
 		for (unsigned j = 0; j < E; j++) { out.template set<U>(j, lookup(in.template get<DI>(j))); }
 		return out;
@@ -91,7 +89,7 @@ struct dictionary_decoder {
 template <unsigned IndexSize, unsigned U, unsigned C, int Model, unsigned ModelIndexSize>
 struct frame_of_reference_decoder {
 	using size_t_ = size_type<IndexSize>;
-	static constexpr unsigned E = 16 / U;
+	static constexpr unsigned E = piece_bytes / U;
 	static constexpr unsigned in_bytes = E * C;
 	static constexpr unsigned dim = (Model == model_linear) ? 2 : 1;
 	uint_t<U>*       __restrict__ decompressed;
@@ -101,20 +99,20 @@ struct frame_of_reference_decoder {
 
 	__device__ __forceinline__ frame_of_reference_decoder(uint_t<U>* out, const int_t<C>* in, const int32_t* c, size_t_ segment_length) :
 		decompressed(out), compressed_input(in), coefficients(c), locator(segment_length) { }
-	__device__ __forceinline__ bool vectorizable() const { return is_aligned_to(decompressed, 16) && is_aligned_to(compressed_input, in_bytes); }
-	__device__ __forceinline__ byte_pack<in_bytes> load(uint64_t v) const { return load_pack<in_bytes>(compressed_input + v * E); }
+	__device__ __forceinline__ bool vectorizable() const { return is_aligned_to(decompressed, piece_bytes) && is_aligned_to(compressed_input, in_bytes < 16 ? in_bytes : 16); }
+	__device__ __forceinline__ byte_pack<in_bytes> load(uint64_t p) const { return load_pack<in_bytes>(compressed_input + p * E); }
 	__device__ __forceinline__ void load_coefficients(int32_t (&c)[dim], size_t_ s) const
 	{
 		#pragma unroll
 		for (unsigned d = 0; d < dim; d++) { c[d] = __ldg(coefficients + (size_t) s * dim + d); }
 	}
-	__device__ __forceinline__ byte_pack<16> decode(const byte_pack<in_bytes>& in, uint64_t v) const
+	__device__ __forceinline__ byte_pack<piece_bytes> decode(const byte_pack<in_bytes>& in, uint64_t p) const
 	{
 		size_t_ s, x;
-		locator.locate((size_t_)(v * E), s, x);
+		locator.locate((size_t_)(p * E), s, x);
 		int32_t c[dim];
 		load_coefficients(c, s);
-		byte_pack<16> out;
+		byte_pack<piece_bytes> out;
 		#pragma unroll
 		for (unsigned j = 0; j < E; j++) {
 			const uint_t<U> predicted = detail::evaluate_model<Model, ModelIndexSize, int32_t, U>(c, x);
@@ -135,37 +133,10 @@ struct frame_of_reference_decoder {
 	}
 };
 
-// out[element] = value for an element number known only at run time, with masks rather than a branch or an indexed
-// access per candidate (which the compiler turns into a round trip through local memory).
-template <unsigned U>
-__device__ __forceinline__ void replace_element(byte_pack<16>& out, unsigned element, uint_t<U> value)
-{
-	constexpr unsigned per_word = (U >= 4) ? 1 : 4 / U; // elements per 32-bit word
-	#pragma unroll
-	for (unsigned w = 0; w < 4; w++) {
-		uint32_t mask, bits;
-		if (U == 8) {
-			mask = (element == w / 2) ? 0xffffffffu : 0u;
-			bits = (w % 2) ? (uint32_t)((uint64_t) value >> 32) : (uint32_t) value;
-		}
-		else if (U == 4) {
-			mask = (element == w) ? 0xffffffffu : 0u;
-			bits = (uint32_t) value;
-		}
-		else {
-			const unsigned shift = (element % per_word) * 8 * U;
-			const uint32_t field = (U == 2) ? 0xffffu : 0xffu;
-			mask = (element / per_word == w) ? (field << shift) : 0u;
-			bits = (uint32_t) value << shift;
-		}
-		out.u32[w] = (out.u32[w] & ~mask) | (bits & mask);
-	}
-}
-
 // ---- the tile index -----------------------------------------------------------------------------------
 
 // ranges[t] = { first, past_last }: tile t's patches are [first, past_last) of the (ascending) patch list; tiles without
-// patches keep the zeroes the launcher filled the array with.  One thread per patch, no loops: patch j opens its tile's
+// patches keep what the launcher filled the array with (all ones: first == past_last).  One thread per patch, no loops: patch j opens its tile's
 // range if its predecessor lies in an earlier tile and closes it if its successor lies in a later one.  Positions at or
 // beyond `length` (a list which is not what it should be) open and close nothing and are never applied.
 template <unsigned IndexSize>
@@ -179,30 +150,105 @@ __global__ void patch_tile_ranges(
 	unsigned                                 log2_tile_elements,
 	uint64_t                                 length)
 {
-	for (uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; j < num_patches; j += (uint64_t) gridDim.x * blockDim.x) {
-		const uint64_t position = __ldg(positions + j);
-		if (position >= length) { continue; }
-		const uint64_t tile = position >> log2_tile_elements;
-		const bool opens = j == 0 || ((uint64_t) __ldg(positions + j - 1) >> log2_tile_elements) != tile;
-		const bool closes = j + 1 == num_patches || ((uint64_t) __ldg(positions + j + 1) >> log2_tile_elements) != tile;
-		if (opens) { ranges[tile].first = (size_type<IndexSize>) j; }
-		if (closes) { ranges[tile].past_last = (size_type<IndexSize>)(j + 1); }
+	// a thread takes 4 consecutive patches (one 16-byte load of 32-bit positions) and their two neighbours
+	constexpr unsigned per_thread = 4;
+	const bool wide = IndexSize == 4 && is_aligned_to(positions, 16);
+	for (uint64_t j0 = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) * per_thread; j0 < num_patches; j0 += (uint64_t) gridDim.x * blockDim.x * per_thread) {
+		uint64_t p[per_thread + 2]; // p[1 + u] = position of patch j0 + u; p[0], p[5]: the neighbours
+		const unsigned count = (unsigned) minimum<uint64_t>(per_thread, num_patches - j0);
+		if (wide && count == per_thread) {
+			const uint4 v = __ldg(reinterpret_cast<const uint4*>(positions + j0));
+			p[1] = v.x; p[2] = v.y; p[3] = v.z; p[4] = v.w;
+		}
+		else {
+			#pragma unroll
+			for (unsigned u = 0; u < per_thread; u++) { p[1 + u] = (u < count) ? (uint64_t) __ldg(positions + j0 + u) : ~0ull; }
+		}
+		p[0] = (j0 == 0) ? ~0ull : (uint64_t) __ldg(positions + j0 - 1);
+		p[per_thread + 1] = (j0 + per_thread < num_patches) ? (uint64_t) __ldg(positions + j0 + per_thread) : ~0ull;
+		#pragma unroll
+		for (unsigned u = 0; u < per_thread; u++) {
+			if (u >= count || p[1 + u] >= length) { continue; }
+			const uint64_t tile = p[1 + u] >> log2_tile_elements;
+			const uint64_t previous = (u == 0) ? p[0] : p[u];
+			const uint64_t next = (u + 1 < count) ? p[2 + u] : ((u + 1 == per_thread) ? p[per_thread + 1] : ~0ull);
+			const bool opens = (j0 + u == 0) || (previous >> log2_tile_elements) != tile;
+			const bool closes = (j0 + u + 1 == num_patches) || (next >> log2_tile_elements) != tile;
+			if (opens) { ranges[tile].first = (size_type<IndexSize>)(j0 + u); }
+			if (closes) { ranges[tile].past_last = (size_type<IndexSize>)(j0 + u + 1); }
+		}
+	}
+}
+
+// The run-compressed positions of a compressed-indices patch list (reference compressed_indices_scatter.cuh:133-231) as a
+// plain list: positions[k] is where patch value k goes.  The same walk as scatter.cuh's expand_compressed_indices, but a whole
+// BLOCK per anchoring period -- its warps share the staged run metadata and take the period's batches of patches in turn --
+// since a column's patch list has too few periods (2.6 K for BASELINE configs[4]) to fill the device with a warp each.
+template <unsigned OutputIndexSize, unsigned InputIndexSize, unsigned RunLengthSize>
+__global__ void expand_compressed_indices_by_block(
+	uint_t<OutputIndexSize>*        __restrict__  positions,
+	const uint_t<RunLengthSize>*    __restrict__  scatter_position_run_lengths,
+	const unsigned char*            __restrict__  scatter_position_run_individual_offset_sizes,
+	const uint_t<OutputIndexSize>*  __restrict__  scatter_position_run_baseline_values,
+	const uint_t<InputIndexSize>*   __restrict__  scatter_position_run_offsets_start_positions,
+	const unsigned char*            __restrict__  scatter_position_offset_bytes,
+	const uint_t<InputIndexSize>*   __restrict__  scatter_position_anchors,
+	uint64_t                                      anchoring_period,
+	uint64_t                                      num_scatter_position_runs,
+	uint64_t                                      data_length)
+{
+	constexpr unsigned batch = 4; // patches per lane with their offset loads in flight at once
+	__shared__ ci_detail::staged_runs_t staged;
+	__shared__ uint64_t chunk_patches_shared;
+	const unsigned lane = lane_index(), warp = warp_index_in_block();
+	const uint64_t num_periods = (data_length + anchoring_period - 1) / anchoring_period;
+	for (uint64_t period = blockIdx.x; period < num_periods; period += gridDim.x) {
+		const uint64_t first_run = __ldg(scatter_position_anchors + period);
+		const bool reaches_end = (period + 1) * anchoring_period >= data_length;
+		const uint64_t past_last_run = reaches_end ? num_scatter_position_runs : (uint64_t) __ldg(scatter_position_anchors + period + 1);
+		uint64_t next_value = period * anchoring_period;
+		for (uint64_t chunk_first_run = first_run; chunk_first_run < past_last_run && next_value < data_length; chunk_first_run += warp_size) {
+			__syncthreads(); // every warp is done with the previous chunk
+			if (warp == 0) {
+				const uint64_t run = chunk_first_run + lane;
+				const bool valid = run < past_last_run;
+				const uint64_t my_length = valid ? (uint64_t) __ldg(scatter_position_run_lengths + run) : 0;
+				staged.widths[lane]        = valid ? (uint8_t)(__ldg(scatter_position_run_individual_offset_sizes + run) / 8) : (uint8_t) 1;
+				staged.baselines[lane]     = valid ? (uint64_t) __ldg(scatter_position_run_baseline_values + run) : 0;
+				staged.offset_starts[lane] = valid ? (uint64_t) __ldg(scatter_position_run_offsets_start_positions + run) * OutputIndexSize : 0;
+				const uint64_t inclusive = warp_inclusive_sum(my_length);
+				staged.ends[lane] = inclusive;
+				if (lane == warp_size - 1) { chunk_patches_shared = inclusive; }
+			}
+			__syncthreads();
+			const uint64_t chunk_patches = chunk_patches_shared;
+			const uint64_t limit = minimum<uint64_t>(chunk_patches, data_length - next_value);
+			for (uint64_t q0 = (uint64_t) warp * warp_size * batch; q0 < limit; q0 += (uint64_t) warps_per_block() * warp_size * batch) {
+				uint_t<OutputIndexSize> decoded[batch];
+				#pragma unroll
+				for (unsigned u = 0; u < batch; u++) {
+					const uint64_t q = q0 + u * warp_size + lane;
+					if (q < limit) {
+						unsigned r = 0; // the first staged run whose end exceeds q
+						#pragma unroll
+						for (unsigned step = warp_size / 2; step > 0; step >>= 1) { if (staged.ends[r + step - 1] <= q) { r += step; } }
+						const uint64_t j = q - (r == 0 ? 0 : staged.ends[r - 1]);
+						decoded[u] = (uint_t<OutputIndexSize>)(staged.baselines[r] +
+							ci_detail::load_offset(scatter_position_offset_bytes + staged.offset_starts[r], j, staged.widths[r]));
+					}
+				}
+				#pragma unroll
+				for (unsigned u = 0; u < batch; u++) {
+					const uint64_t q = q0 + u * warp_size + lane;
+					if (q < limit) { positions[next_value + q] = decoded[u]; }
+				}
+			}
+			next_value += chunk_patches;
+		}
 	}
 }
 
 // ---- the tile loop -------------------------------------------------------------------------------------
-
-// What a warp keeps in shared memory to route a tile's patches to the lanes which own the patched vectors:
-//   slots[l * unroll + k]   for vector k * 32 + l of the tile (lane l's k-th vector): 1 + the index, within the tile's patch
-//                           range, of the first patch which falls into that vector, or 0 (16 bytes per lane: one LDS.128);
-//   positions / values      of the tile's first 32 patches (the ones requested ahead), position relative to the tile.
-// ~1 KiB per warp -- the decoded vectors themselves never leave the registers.
-template <unsigned IndexSize, unsigned U>
-struct alignas(16) patch_overlay_t {
-	uint16_t             slots[warp_size * unroll];
-	size_type<IndexSize> positions[warp_size];
-	uint_t<U>            values[warp_size];
-};
 
 template <unsigned IndexSize, unsigned U, typename Decoder>
 __device__ __forceinline__ void decode_and_patch(
@@ -213,19 +259,16 @@ __device__ __forceinline__ void decode_and_patch(
 	unsigned                                      log2_tile_elements,
 	size_type<IndexSize>                          length)
 {
-	// (element, vector and tile numbers are kept in the column's own index width: 32-bit arithmetic -- and half the
+	// (element, piece and tile numbers are kept in the column's own index width: 32-bit arithmetic -- and half the
 	// registers -- for columns of up to 2^32 elements)
 	using index_t = size_type<IndexSize>;
-	constexpr unsigned E = Decoder::E;
-	static_assert(unroll == 8, "a lane's slots are read as one 16-byte vector of 8 x 16 bits");
+	constexpr unsigned E = Decoder::E; // elements per piece
 	uint_t<U>* __restrict__ const decompressed = decoder.decompressed;
 	const unsigned lane = lane_index();
 	const index_t elements_per_tile = (index_t) 1 << log2_tile_elements;
 	const bool vectorizable = elements_per_tile == (index_t)(warp_size * unroll * E) && decoder.vectorizable(); // (the launcher sized the tiles by the same test)
 	const index_t num_tiles = (index_t)(((uint64_t) length + elements_per_tile - 1) >> log2_tile_elements);
-	constexpr unsigned vectors_per_tile = warp_size * unroll;
-	__shared__ patch_overlay_t<IndexSize, U> overlay_of_warp[max_warps_per_block];
-	patch_overlay_t<IndexSize, U>& overlay = overlay_of_warp[warp_index_in_block()];
+	constexpr unsigned pieces_per_tile = warp_size * unroll;
 
 	const uint64_t first_tile = global_warp_index(), tile_stride = num_warps_in_grid();
 	if (first_tile >= num_tiles) { return; }
@@ -236,11 +279,7 @@ __device__ __forceinline__ void decode_and_patch(
 			const uint64_t tile_start = tile << log2_tile_elements;
 			const uint64_t tile_end = minimum<uint64_t>(tile_start + elements_per_tile, length);
 			const patch_range_t<IndexSize> range = tile_ranges[tile];
-			#pragma unroll
-			for (unsigned k = 0; k < unroll; k++) {
-				const uint64_t i = tile_start + k * warp_size + lane;
-				if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
-			}
+			for (uint64_t i = tile_start + lane; i < tile_end; i += warp_size) { decompressed[i] = decoder.decode_one(i); }
 			if (range.past_last > range.first) {
 				__syncwarp();
 				for (uint64_t q = (uint64_t) range.first + lane; q < range.past_last; q += warp_size) {
@@ -253,134 +292,83 @@ __device__ __forceinline__ void decode_and_patch(
 		return;
 	}
 
-	// A warp takes tiles w, w + W, ...  Two of them are in flight at any time: while tile t is decoded, patched and stored,
-	// the compressed vectors and the first 32 patches of tile t + W are on their way (and the patch range of tile t + 2W,
-	// which those requests will need) -- the kernel has registers for few warps, so each must keep more bytes in flight.
-	struct pending_t {
-		index_t                       tile;
-		patch_range_t<IndexSize>      range;
-		byte_pack<Decoder::in_bytes>  in[unroll];
-		uint_t<IndexSize>             position;
-		uint_t<U>                     value;
+	// Lane q holds patch q of the tile (position and value, requested a tile ahead) and stores it right after the tile's pieces
+	// have been stored: the sector it lands in is still dirty in L2, where the partial write merges, so DRAM sees the patched
+	// sector once.  (Measured alternatives, profiles/patched_r02_notes.md: patching the pieces in registers before they are
+	// stored -- by shuffles to the owning lane, or through shared memory -- costs 15-30 instructions per patch in a kernel which is
+	// bound by instruction issue, against ~1 for the store.)
+	struct patches_t { uint_t<IndexSize> position; uint_t<U> value; };
+	const patch_range_t<IndexSize> no_patches = { 0, 0 };
+	auto request_patches = [&](const patch_range_t<IndexSize>& range, index_t chunk_first) {
+		patches_t p = { 0, 0 };
+		if (range.past_last > range.first && chunk_first + lane < range.past_last - range.first) {
+			p.position = __ldg(patch_positions + range.first + chunk_first + lane);
+			p.value = __ldg(patch_values + range.first + chunk_first + lane);
+		}
+		return p;
 	};
-	auto request = [&](pending_t& p) {
-		const index_t tile_start = p.tile << log2_tile_elements;
-		const index_t tile_end = (index_t) minimum<uint64_t>((uint64_t) tile_start + elements_per_tile, length);
-		const index_t first_vector = p.tile * vectors_per_tile;
-		const unsigned num_vectors = (unsigned)(tile_end / E - first_vector);
+
+	index_t tile = (index_t) first_tile;
+	patch_range_t<IndexSize> range = tile_ranges[tile];
+	bool has_next = (uint64_t) tile + tile_stride < num_tiles;
+	patch_range_t<IndexSize> range_next = has_next ? tile_ranges[tile + (index_t) tile_stride] : no_patches;
+	patches_t patches = request_patches(range, 0);
+
+	#pragma unroll 1
+	while (true) {
+		const index_t tile_start = tile << log2_tile_elements;
+		const index_t first_piece = tile * pieces_per_tile;
+		const bool whole = tile + 1 != num_tiles || (uint64_t) tile_start + elements_per_tile == length;
+		const index_t tile_end = whole ? tile_start + elements_per_tile : length;
+		const unsigned num_pieces = whole ? pieces_per_tile : (unsigned)(tile_end / E - first_piece); // all of them but for the column's last tile
+		// 1. the tile's compressed elements
+		byte_pack<Decoder::in_bytes> in[unroll];
 		#pragma unroll
 		for (unsigned k = 0; k < unroll; k++) {
 			const unsigned v = k * warp_size + lane;
-			if (v < num_vectors) { p.in[k] = decoder.load(first_vector + v); }
+			if (v < num_pieces) { in[k] = decoder.load(first_piece + v); }
 		}
-		p.position = 0; p.value = 0;
-		if (p.range.past_last > p.range.first && lane < p.range.past_last - p.range.first) {
-			p.position = __ldg(patch_positions + p.range.first + lane); p.value = __ldg(patch_values + p.range.first + lane);
-		}
-	};
-	auto finish = [&](const pending_t& p) {
-		const index_t tile_start = p.tile << log2_tile_elements;
-		const index_t tile_end = (index_t) minimum<uint64_t>((uint64_t) tile_start + elements_per_tile, length);
-		const index_t first_vector = p.tile * vectors_per_tile;
-		const unsigned num_vectors = (unsigned)(tile_end / E - first_vector); // all of them but for the column's last tile
-		const index_t first_patch = p.range.first, past_last_patch = p.range.past_last;
-		const index_t num_patches = past_last_patch > first_patch ? past_last_patch - first_patch : 0; // uniform over the warp
-		if (num_vectors == vectors_per_tile) {
-			// A patch stored to global memory after the vector which contains it is a partial write of a 32-byte sector:
-			// it merges in L2 (no HBM traffic) but each one still costs L2 a read-modify-write.  So a vector is patched
-			// BEFORE it is stored, in the registers of the lane which owns it.  What that lane needs to know -- which of its
-			// vectors are hit, and by which patches -- goes through the warp's overlay: the lanes holding the patches mark
-			// the slot of the vector they hit, every lane reads its 8 slots with one 16-byte load.  Patches are ascending,
-			// so those of one vector are neighbours in the list: only the first of them marks the slot, and the owner walks
-			// on from there.
-			uint4 my_slots = make_uint4(0u, 0u, 0u, 0u);
-			if (num_patches != 0) {
-				reinterpret_cast<uint4*>(overlay.slots)[lane] = my_slots;
-				__syncwarp();
-				// (a position outside the tile can only come from a list which is not ascending: ignored, not written wild)
-				index_t in_tile = (index_t)(p.position - tile_start);
-				bool valid = lane < num_patches && in_tile < elements_per_tile;
-				if (!valid) { in_tile = ~(index_t) 0; }
-				unsigned vector = (unsigned)(in_tile / E);
-				overlay.positions[lane] = in_tile;
-				overlay.values[lane] = p.value;
-				unsigned previous = __shfl_up_sync(full_mask, vector, 1);
-				if (valid && (lane == 0 || previous != vector)) { overlay.slots[(vector % warp_size) * unroll + vector / warp_size] = (uint16_t)(lane + 1); }
-				// tiles with more than 32 patches: the rest of the list, 32 at a time (their owners will fetch them from global memory)
-				for (index_t base = warp_size; base < num_patches; base += warp_size) {
-					const unsigned carried = __shfl_sync(full_mask, vector, warp_size - 1);
-					const index_t q = base + lane;
-					in_tile = ~(index_t) 0;
-					if (q < num_patches) { in_tile = (index_t)(__ldg(patch_positions + first_patch + q) - tile_start); }
-					valid = in_tile < elements_per_tile;
-					vector = valid ? (unsigned)(in_tile / E) : ~0u;
-					previous = __shfl_up_sync(full_mask, vector, 1);
-					if (lane == 0) { previous = carried; }
-					if (valid && previous != vector && q < 0xffffu) { overlay.slots[(vector % warp_size) * unroll + vector / warp_size] = (uint16_t)(q + 1); }
-				}
-				__syncwarp();
-				my_slots = reinterpret_cast<const uint4*>(overlay.slots)[lane];
-			}
-			const uint32_t slot_words[4] = { my_slots.x, my_slots.y, my_slots.z, my_slots.w };
-			#pragma unroll
-			for (unsigned k = 0; k < unroll; k++) {
-				byte_pack<16> out = decoder.decode(p.in[k], first_vector + k * warp_size + lane);
-				const unsigned slot = (slot_words[k / 2] >> (16 * (k % 2))) & 0xffffu;
-				if (slot != 0) {
-					const unsigned my_vector = k * warp_size + lane;
-					index_t q = slot - 1;
-					do {
-						const index_t in_tile = q < warp_size ? overlay.positions[q] : (index_t)(__ldg(patch_positions + first_patch + q) - tile_start);
-						if (in_tile / E != my_vector) { break; }
-						const uint_t<U> value = q < warp_size ? overlay.values[q] : __ldg(patch_values + first_patch + q);
-						replace_element<U>(out, (unsigned)(in_tile % E), value);
-						q++;
-					} while (q < num_patches);
-				}
-				store_pack_16(decompressed + (uint64_t)(first_vector + k * warp_size + lane) * E, out);
-			}
-			if (num_patches != 0) { __syncwarp(); } // the next tile's patches go to the same overlay
-		}
-		else {
-			#pragma unroll
-			for (unsigned k = 0; k < unroll; k++) {
-				const unsigned v = k * warp_size + lane;
-				if (v < num_vectors) { store_pack_16(decompressed + (uint64_t)(first_vector + v) * E, decoder.decode(p.in[k], first_vector + v)); }
-			}
-			// the column's < E trailing elements (in its last tile only)
-			const uint64_t i = (uint64_t)(first_vector + num_vectors) * E + lane;
-			if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
-			if (num_patches != 0) { // the column's last, partial tile: patches stored after their vectors
-				__syncwarp(); // orders the tile's stores before the patch stores
-				if (lane < num_patches && (index_t)(p.position - tile_start) < tile_end - tile_start) { decompressed[p.position] = p.value; }
-				for (uint64_t q = (uint64_t) first_patch + warp_size + lane; q < past_last_patch; q += warp_size) {
-					const index_t position = __ldg(patch_positions + q);
-					if ((index_t)(position - tile_start) < tile_end - tile_start) { decompressed[position] = __ldg(patch_values + q); }
-				}
-			}
-		}
-	};
-
-	pending_t current, next;
-	current.tile = (index_t) first_tile;
-	current.range = tile_ranges[first_tile];
-	request(current);
-	bool has_next = first_tile + tile_stride < num_tiles;
-	patch_range_t<IndexSize> range_after = current.range;
-	if (has_next) { range_after = tile_ranges[first_tile + tile_stride]; }
-	#pragma unroll 1
-	while (true) {
+		// 2. one tile ahead: the next tile's first 32 patches; two ahead: the range of the tile after it
+		patches_t patches_next = { 0, 0 };
+		patch_range_t<IndexSize> range_after = no_patches;
 		bool has_after = false;
 		if (has_next) {
-			next.tile = current.tile + (index_t) tile_stride;
-			next.range = range_after;
-			request(next);
-			has_after = (uint64_t) next.tile + tile_stride < num_tiles;
-			if (has_after) { range_after = tile_ranges[next.tile + (index_t) tile_stride]; }
+			patches_next = request_patches(range_next, 0);
+			has_after = (uint64_t) tile + 2 * tile_stride < num_tiles;
+			if (has_after) { range_after = tile_ranges[tile + (index_t)(2 * tile_stride)]; }
 		}
-		finish(current);
+		// 3. decode
+		byte_pack<piece_bytes> out[unroll];
+		#pragma unroll
+		for (unsigned k = 0; k < unroll; k++) {
+			const unsigned v = k * warp_size + lane;
+			if (v < num_pieces) { out[k] = decoder.decode(in[k], first_piece + v); }
+		}
+		const index_t num_patches = range.past_last > range.first ? range.past_last - range.first : 0; // uniform over the warp
+		// 4. store
+		#pragma unroll
+		for (unsigned k = 0; k < unroll; k++) {
+			const unsigned v = k * warp_size + lane;
+			if (v < num_pieces) { store_piece(decompressed + (uint64_t)(first_piece + v) * E, out[k]); }
+		}
+		// 5. the patches, after the pieces they fall into (ordered behind them by the warp barrier): partial writes of sectors which
+		// L2 still holds, merged there -- no HBM traffic
+		if (!whole) {
+			const uint64_t i = (uint64_t)(first_piece + num_pieces) * E + lane;
+			if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
+		}
+		if (num_patches != 0) {
+			__syncwarp();
+			if (lane < num_patches && (index_t)(patches.position - tile_start) < tile_end - tile_start) { decompressed[patches.position] = patches.value; }
+			for (uint64_t q = (uint64_t) range.first + warp_size + lane; q < range.past_last; q += warp_size) { // (tiles with more than 32 patches)
+				const index_t position = __ldg(patch_positions + q);
+				if ((index_t)(position - tile_start) < tile_end - tile_start) { decompressed[position] = __ldg(patch_values + q); }
+			}
+		}
 		if (!has_next) { break; }
-		current = next;
+		tile += (index_t) tile_stride;
+		range = range_next; range_next = range_after;
+		patches = patches_next;
 		has_next = has_after;
 	}
 }
@@ -407,11 +395,17 @@ __global__ void __launch_bounds__(GIDDY_ELEMENTWISE_BLOCK_THREADS, patched_detai
 	const patched_detail::patch_range_t<IndexSize>*  __restrict__  tile_ranges,
 	unsigned                                          log2_tile_elements)
 {
-	patched_detail::dictionary_decoder<IndexSize, U, DictionaryIndexSize> decoder;
-	decoder.decompressed = decompressed;
-	decoder.compressed_input = compressed_input;
-	decoder.setup(dictionary_entries, num_dictionary_entries, cache_dictionary_in_shared_memory);
-	patched_detail::decode_and_patch<IndexSize, U>(decoder, patch_data, patch_indices, tile_ranges, log2_tile_elements, length);
+	if (cache_dictionary_in_shared_memory) {
+		auto cached = reinterpret_cast<uint_t<U>*>(dynamic_shared_memory);
+		for (uint64_t i = threadIdx.x; i < num_dictionary_entries; i += blockDim.x) { cached[i] = __ldg(dictionary_entries + i); }
+		__syncthreads();
+		const patched_detail::dictionary_decoder<IndexSize, U, DictionaryIndexSize, true> decoder { decompressed, compressed_input, cached };
+		patched_detail::decode_and_patch<IndexSize, U>(decoder, patch_data, patch_indices, tile_ranges, log2_tile_elements, length);
+	}
+	else {
+		const patched_detail::dictionary_decoder<IndexSize, U, DictionaryIndexSize, false> decoder { decompressed, compressed_input, dictionary_entries };
+		patched_detail::decode_and_patch<IndexSize, U>(decoder, patch_data, patch_indices, tile_ranges, log2_tile_elements, length);
+	}
 }
 
 // -------------------------------------------------------------------------------------------------

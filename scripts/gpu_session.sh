@@ -36,13 +36,22 @@ variants)
 		name=$(basename $(dirname $lib)); echo "--- $name" | tee -a $OUT/${TAG}_variants.txt
 		timeout 600 python benchmarks/configs.py --only cfg3,cfg5 --no-reference --library $lib --out $OUT/${TAG}_variant_$name.json 2>&1 | grep -i "fused\|Dictionary u8\|FOR linear" | tee -a $OUT/${TAG}_variants.txt
 	done ;;
+patchedtests)
+	timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_sharding_gpu.py -m gpu -x -q -k "patched or fused" 2>&1 | tail -15 > $OUT/${TAG}_pytest_patched.txt
+	tail -4 $OUT/${TAG}_pytest_patched.txt ;;
+launches_patched)
+	timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches_patched.csv -k "regex:patch|expand|dictionary|frame_of" \
+		python benchmarks/configs.py --only cfg3,cfg5 --no-reference --repeats 2 --library ${VARIANT_LIB:-libgiddy_b200/lib/libgiddy_b200.so} > $OUT/${TAG}_launches_patched.log 2>&1
+	python scripts/launch_list_summary.py $OUT/${TAG}_launches_patched.csv $OUT/${TAG}_launches_patched.md; cat $OUT/${TAG}_launches_patched.md | cut -c1-220 ;;
+probe)
+	timeout 900 python benchmarks/patched_probe.py --out $OUT/${TAG}_patched_probe.json 2>&1 | tee $OUT/${TAG}_patched_probe.txt ;;
 configs)
 	timeout 1500 python benchmarks/configs.py --out $OUT/${TAG}_configs.json 2>&1 | tee $OUT/${TAG}_configs.txt ;;
 sweep)
 	timeout 1500 python benchmarks/sweep.py --log2-n 27 --out $OUT/${TAG}_sweep.json 2>&1 | tee $OUT/${TAG}_sweep.txt | tail -70 ;;
 ncu_patched)
-	timeout 900 ncu --set full --clock-control none --import-source on -k "regex:patched_|patch_tile|expand_compressed" -f -o $OUT/${TAG}_patched \
-		python benchmarks/configs.py --only cfg3,cfg5 --no-reference --repeats 1 > $OUT/${TAG}_ncu_patched.log 2>&1
+	timeout 900 ncu --set full --clock-control none --import-source on -k "regex:patched_|patch_tile|expand_compressed" -c ${NCU_COUNT:-40} -f -o $OUT/${TAG}_patched \
+		python benchmarks/configs.py --only cfg3,cfg5 --no-reference --repeats 1 --library ${VARIANT_LIB:-libgiddy_b200/lib/libgiddy_b200.so} > $OUT/${TAG}_ncu_patched.log 2>&1
 	ls -la $OUT/${TAG}_patched.ncu-rep ;;
 ncu_all)
 	timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:decompress|scatter|compress|encode" -f -o $OUT/${TAG}_schemes \
