@@ -104,21 +104,40 @@ giddy_status_t for_launch(void* stream, const giddy_launch_config_t* cfg, void* 
 	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocFromPoolAsync (patch positions and tile index)"); }
 	void* positions = static_cast<unsigned char*>(workspace) + offsets_bytes;
 	giddy_status_t status = GIDDY_SUCCESS;
-	// one fill for both: index entries of all ones are empty ranges, and positions of all ones lie beyond any column (runs
-	// which cover fewer than data_length patches leave the rest of the list never applied, as the reference's kernel would)
-	error = cudaMemsetAsync(workspace, 0xff, offsets_bytes + data_length * I, s);
+	// index entries of all ones are empty ranges; positions of all ones lie beyond any column (runs which cover fewer than
+	// data_length patches leave the rest of the list never applied, as the reference's kernel would).  The fused kernel fills
+	// the uncovered positions itself; the generic path needs the whole list filled beforehand.
+	const bool fused_index = data_length != 0 && anchoring_period * I <= 32 * 1024;
+	error = cudaMemsetAsync(workspace, 0xff, fused_index ? offsets_bytes : offsets_bytes + data_length * I, s);
 	if (error != cudaSuccess) { cudaFreeAsync(workspace, s); return fail_cuda(error, "cudaMemsetAsync (patch positions and tile index)"); }
+	bool index_built = false;
 	if (data_length != 0) {
 		const uint64_t periods = (data_length + anchoring_period - 1) / anchoring_period;
-		kernels::patched_detail::expand_compressed_indices_by_block<I, II, II><<<(unsigned) (periods < 0x7fffffffull ? periods : 0x7fffffffull), 64, 0, s>>>(
-			static_cast<uint_t<I>*>(positions), static_cast<const uint_t<II>*>(run_lengths), static_cast<const unsigned char*>(offset_sizes),
-			static_cast<const uint_t<I>*>(baselines), static_cast<const uint_t<II>*>(offsets_start),
-			static_cast<const unsigned char*>(offset_bytes), static_cast<const uint_t<II>*>(anchors),
-			anchoring_period, num_runs, data_length);
+		// periods whose decoded positions fit 32 KiB keep them in shared memory and build the tile index in the same kernel
+		// (one launch and one pass over the positions less); longer ones leave it to patch_tile_ranges
+		if (fused_index) {
+			kernels::patched_detail::expand_and_index_compressed_indices<I, II, II><<<(unsigned) (periods < 0x7fffffffull ? periods : 0x7fffffffull), 128,
+				(unsigned)(anchoring_period * I), s>>>(
+				static_cast<uint_t<I>*>(positions), static_cast<kernels::patched_detail::patch_range_t<I>*>(workspace),
+				static_cast<const uint_t<II>*>(run_lengths), static_cast<const unsigned char*>(offset_sizes),
+				static_cast<const uint_t<I>*>(baselines), static_cast<const uint_t<II>*>(offsets_start),
+				static_cast<const unsigned char*>(offset_bytes), static_cast<const uint_t<II>*>(anchors),
+				(unsigned) anchoring_period, num_runs, data_length, log2_tile, n);
+		}
+		else {
+			const unsigned warps_per_block = GIDDY_CI_SCATTER_WARPS_PER_BLOCK;
+			const uint64_t blocks = (periods + warps_per_block - 1) / warps_per_block;
+			kernels::expand_compressed_indices<I, II, II><<<(unsigned) (blocks < 0x7fffffffull ? blocks : 0x7fffffffull), warps_per_block * 32, 0, s>>>(
+				static_cast<uint_t<I>*>(positions), static_cast<const uint_t<II>*>(run_lengths), static_cast<const unsigned char*>(offset_sizes),
+				static_cast<const uint_t<I>*>(baselines), static_cast<const uint_t<II>*>(offsets_start),
+				static_cast<const unsigned char*>(offset_bytes), static_cast<const uint_t<II>*>(anchors),
+				(uint_t<II>) anchoring_period, (uint_t<II>) num_runs, (size_type<II>) data_length);
+		}
 		error = cudaGetLastError();
 		if (error != cudaSuccess) { status = fail_cuda(error, "kernel launch (patch position decode)"); }
+		index_built = fused_index;
 	}
-	if (status == GIDDY_SUCCESS) { status = build_tile_index<I>(s, workspace, positions, data_length, log2_tile, num_tiles, n); }
+	if (status == GIDDY_SUCCESS && !index_built) { status = build_tile_index<I>(s, workspace, positions, data_length, log2_tile, num_tiles, n); }
 	if (status == GIDDY_SUCCESS) {
 		status = launch(kernels::patched_frame_of_reference_decompress<I, U, C, M, MI>, stream, cfg,
 			static_cast<uint_t<U>*>(out), static_cast<const int_t<C>*>(in), static_cast<const int32_t*>(coeffs),

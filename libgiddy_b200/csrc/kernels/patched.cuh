@@ -181,70 +181,124 @@ __global__ void patch_tile_ranges(
 }
 
 // The run-compressed positions of a compressed-indices patch list (reference compressed_indices_scatter.cuh:133-231) as a
-// plain list: positions[k] is where patch value k goes.  The same walk as scatter.cuh's expand_compressed_indices, but a whole
-// BLOCK per anchoring period -- its warps share the staged run metadata and take the period's batches of patches in turn --
-// since a column's patch list has too few periods (2.6 K for BASELINE configs[4]) to fill the device with a warp each.
+// plain list -- positions[k] is where patch value k goes -- AND the tile index of those positions, in one kernel, for lists
+// whose anchoring period is short enough for a period's positions to sit in shared memory (the launcher checks).  A BLOCK
+// per anchoring period: a column's patch list has too few periods (2.6 K for BASELINE configs[4]) to fill the device with a
+// warp each.  The run metadata of up to 32 runs is staged at a time (one run per lane of the first warp, a warp scan of the
+// run lengths); the runs' patches are then one flat list, each patch finding its run by a 5-step search of the scanned
+// lengths.  Everything per patch is 32-bit arithmetic: the kernel is bound by instruction issue, not by bytes.
+// (Lists with longer periods go through scatter.cuh's expand_compressed_indices and patch_tile_ranges.)
 template <unsigned OutputIndexSize, unsigned InputIndexSize, unsigned RunLengthSize>
-__global__ void expand_compressed_indices_by_block(
+__global__ void expand_and_index_compressed_indices(
 	uint_t<OutputIndexSize>*        __restrict__  positions,
+	patch_range_t<OutputIndexSize>* __restrict__  ranges,
 	const uint_t<RunLengthSize>*    __restrict__  scatter_position_run_lengths,
 	const unsigned char*            __restrict__  scatter_position_run_individual_offset_sizes,
 	const uint_t<OutputIndexSize>*  __restrict__  scatter_position_run_baseline_values,
 	const uint_t<InputIndexSize>*   __restrict__  scatter_position_run_offsets_start_positions,
 	const unsigned char*            __restrict__  scatter_position_offset_bytes,
 	const uint_t<InputIndexSize>*   __restrict__  scatter_position_anchors,
-	uint64_t                                      anchoring_period,
+	unsigned                                      anchoring_period,
 	uint64_t                                      num_scatter_position_runs,
-	uint64_t                                      data_length)
+	uint64_t                                      data_length,
+	unsigned                                      log2_tile_elements,
+	uint64_t                                      length)
 {
-	constexpr unsigned batch = 4; // patches per lane with their offset loads in flight at once
-	__shared__ ci_detail::staged_runs_t staged;
-	__shared__ uint64_t chunk_patches_shared;
+	using position_t = uint_t<OutputIndexSize>;
+	constexpr unsigned batch = 8; // patches per lane with their offset loads in flight at once
+	__shared__ uint32_t   ends[warp_size];           // inclusive scan of the staged runs' lengths
+	__shared__ position_t baselines[warp_size];
+	__shared__ uint32_t   offset_starts[warp_size];  // byte offset of the run's first offset, relative to the chunk's first run's
+	__shared__ uint8_t    widths[warp_size];         // bytes per offset
+	__shared__ uint64_t   chunk_offsets_base;
+	__shared__ position_t neighbours[2];             // positions of the patch before the period's first and after its last
+	__shared__ bool       has_neighbour[2];
+	position_t* const period_positions = reinterpret_cast<position_t*>(dynamic_shared_memory); // anchoring_period entries
 	const unsigned lane = lane_index(), warp = warp_index_in_block();
 	const uint64_t num_periods = (data_length + anchoring_period - 1) / anchoring_period;
 	for (uint64_t period = blockIdx.x; period < num_periods; period += gridDim.x) {
+		const uint64_t period_first = period * anchoring_period;
+		const unsigned period_patches = (unsigned) minimum<uint64_t>(anchoring_period, data_length - period_first);
 		const uint64_t first_run = __ldg(scatter_position_anchors + period);
-		const bool reaches_end = (period + 1) * anchoring_period >= data_length;
-		const uint64_t past_last_run = reaches_end ? num_scatter_position_runs : (uint64_t) __ldg(scatter_position_anchors + period + 1);
-		uint64_t next_value = period * anchoring_period;
-		for (uint64_t chunk_first_run = first_run; chunk_first_run < past_last_run && next_value < data_length; chunk_first_run += warp_size) {
+		const uint64_t past_last_run = (period + 1 == num_periods) ? num_scatter_position_runs : (uint64_t) __ldg(scatter_position_anchors + period + 1);
+		if (threadIdx.x >= blockDim.x - 2) {
+			// the neighbours across the period's ends, decoded from their runs (runs never straddle a period): the last patch of
+			// run first_run - 1, the first of run past_last_run -- by two threads of the LAST warp, overlapping the staging
+			const bool before = threadIdx.x == blockDim.x - 2;
+			const bool exists = before ? first_run > 0 : past_last_run < num_scatter_position_runs;
+			position_t position = 0;
+			if (exists) {
+				const uint64_t run = before ? first_run - 1 : past_last_run;
+				const uint64_t j = before ? (uint64_t) __ldg(scatter_position_run_lengths + run) - 1 : 0;
+				position = (position_t)((uint64_t) __ldg(scatter_position_run_baseline_values + run) + ci_detail::load_offset(
+					scatter_position_offset_bytes + (uint64_t) __ldg(scatter_position_run_offsets_start_positions + run) * OutputIndexSize, j,
+					__ldg(scatter_position_run_individual_offset_sizes + run) / 8));
+			}
+			neighbours[before ? 0 : 1] = position;
+			has_neighbour[before ? 0 : 1] = exists;
+		}
+		unsigned done = 0; // patches of the period decoded so far
+		for (uint64_t chunk_first_run = first_run; chunk_first_run < past_last_run && done < period_patches; chunk_first_run += warp_size) {
 			__syncthreads(); // every warp is done with the previous chunk
 			if (warp == 0) {
 				const uint64_t run = chunk_first_run + lane;
 				const bool valid = run < past_last_run;
-				const uint64_t my_length = valid ? (uint64_t) __ldg(scatter_position_run_lengths + run) : 0;
-				staged.widths[lane]        = valid ? (uint8_t)(__ldg(scatter_position_run_individual_offset_sizes + run) / 8) : (uint8_t) 1;
-				staged.baselines[lane]     = valid ? (uint64_t) __ldg(scatter_position_run_baseline_values + run) : 0;
-				staged.offset_starts[lane] = valid ? (uint64_t) __ldg(scatter_position_run_offsets_start_positions + run) * OutputIndexSize : 0;
-				const uint64_t inclusive = warp_inclusive_sum(my_length);
-				staged.ends[lane] = inclusive;
-				if (lane == warp_size - 1) { chunk_patches_shared = inclusive; }
+				const uint32_t my_length = valid ? (uint32_t) minimum<uint64_t>(__ldg(scatter_position_run_lengths + run), anchoring_period) : 0u;
+				const uint64_t start = valid ? (uint64_t) __ldg(scatter_position_run_offsets_start_positions + run) * OutputIndexSize : 0;
+				const uint64_t chunk_start = shuffle_from(start, 0);
+				widths[lane]        = valid ? (uint8_t)(__ldg(scatter_position_run_individual_offset_sizes + run) / 8) : (uint8_t) 1;
+				baselines[lane]     = valid ? (position_t) __ldg(scatter_position_run_baseline_values + run) : (position_t) 0;
+				offset_starts[lane] = (uint32_t)(start - chunk_start);
+				ends[lane] = warp_inclusive_sum(my_length); // (lanes without a run repeat the total: the search never lands on them)
+				if (lane == 0) { chunk_offsets_base = chunk_start; }
 			}
 			__syncthreads();
-			const uint64_t chunk_patches = chunk_patches_shared;
-			const uint64_t limit = minimum<uint64_t>(chunk_patches, data_length - next_value);
-			for (uint64_t q0 = (uint64_t) warp * warp_size * batch; q0 < limit; q0 += (uint64_t) warps_per_block() * warp_size * batch) {
-				uint_t<OutputIndexSize> decoded[batch];
+			const unsigned chunk_patches = minimum<unsigned>(ends[warp_size - 1], period_patches - done);
+			const uint8_t* __restrict__ const chunk_offsets = scatter_position_offset_bytes + chunk_offsets_base;
+			for (unsigned q0 = warp * warp_size * batch; q0 < chunk_patches; q0 += warps_per_block() * warp_size * batch) {
+				position_t decoded[batch];
 				#pragma unroll
 				for (unsigned u = 0; u < batch; u++) {
-					const uint64_t q = q0 + u * warp_size + lane;
-					if (q < limit) {
+					const unsigned q = q0 + u * warp_size + lane;
+					if (q < chunk_patches) {
 						unsigned r = 0; // the first staged run whose end exceeds q
 						#pragma unroll
-						for (unsigned step = warp_size / 2; step > 0; step >>= 1) { if (staged.ends[r + step - 1] <= q) { r += step; } }
-						const uint64_t j = q - (r == 0 ? 0 : staged.ends[r - 1]);
-						decoded[u] = (uint_t<OutputIndexSize>)(staged.baselines[r] +
-							ci_detail::load_offset(scatter_position_offset_bytes + staged.offset_starts[r], j, staged.widths[r]));
+						for (unsigned step = warp_size / 2; step > 0; step >>= 1) { if (ends[r + step - 1] <= q) { r += step; } }
+						const unsigned j = q - (r == 0 ? 0u : ends[r - 1]);
+						const unsigned width = widths[r];
+						const uint8_t* const at = chunk_offsets + (offset_starts[r] + j * width);
+						position_t offset;
+						if (width == 1) { offset = __ldg(at); }
+						else if (width == 2) { offset = __ldg(reinterpret_cast<const uint16_t*>(at)); }
+						else if (width == 4 || OutputIndexSize <= 4) { offset = (position_t) __ldg(reinterpret_cast<const uint32_t*>(at)); }
+						else { offset = (position_t)((uint64_t) __ldg(reinterpret_cast<const uint32_t*>(at)) | ((uint64_t) __ldg(reinterpret_cast<const uint32_t*>(at) + 1) << 32)); }
+						decoded[u] = (position_t)(baselines[r] + offset);
 					}
 				}
 				#pragma unroll
 				for (unsigned u = 0; u < batch; u++) {
-					const uint64_t q = q0 + u * warp_size + lane;
-					if (q < limit) { positions[next_value + q] = decoded[u]; }
+					const unsigned q = q0 + u * warp_size + lane;
+					if (q < chunk_patches) { positions[period_first + done + q] = decoded[u]; period_positions[done + q] = decoded[u]; }
 				}
 			}
-			next_value += chunk_patches;
+			done += chunk_patches;
 		}
+		// (runs which cover fewer patches than the period holds -- a malformed list -- leave the rest at a position beyond any
+		// column: never applied, as the reference's kernel would skip them)
+		for (unsigned k = done + threadIdx.x; k < period_patches; k += blockDim.x) { positions[period_first + k] = ~(position_t) 0; }
+		// the tile index for this period's patches (see patch_tile_ranges): patch k opens its tile's range if its predecessor lies
+		// in an earlier tile and closes it if its successor lies in a later one
+		__syncthreads();
+		for (unsigned k = threadIdx.x; k < done; k += blockDim.x) {
+			const position_t position = period_positions[k];
+			if ((uint64_t) position >= length) { continue; }
+			const position_t tile = position >> log2_tile_elements;
+			const bool opens = (k == 0) ? (!has_neighbour[0] || (neighbours[0] >> log2_tile_elements) != tile) : (period_positions[k - 1] >> log2_tile_elements) != tile;
+			const bool closes = (k + 1 == done) ? (!has_neighbour[1] || (neighbours[1] >> log2_tile_elements) != tile) : (period_positions[k + 1] >> log2_tile_elements) != tile;
+			if (opens) { ranges[tile].first = (size_type<OutputIndexSize>)(period_first + k); }
+			if (closes) { ranges[tile].past_last = (size_type<OutputIndexSize>)(period_first + k + 1); }
+		}
+		__syncthreads(); // before the next period overwrites the positions
 	}
 }
 

@@ -43,6 +43,11 @@ launches_patched)
 	timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches_patched.csv -k "regex:patch|expand|dictionary|frame_of" \
 		python benchmarks/configs.py --only cfg3,cfg5 --no-reference --repeats 2 --library ${VARIANT_LIB:-libgiddy_b200/lib/libgiddy_b200.so} > $OUT/${TAG}_launches_patched.log 2>&1
 	python scripts/launch_list_summary.py $OUT/${TAG}_launches_patched.csv $OUT/${TAG}_launches_patched.md; cat $OUT/${TAG}_launches_patched.md | cut -c1-220 ;;
+ncu_kernel)
+	# NCU_KERNEL=<regex> NCU_COUNT=<n> NCU_CMD="python ..." : a full capture of a few launches of one kernel
+	timeout 900 ncu --set full --clock-control none --import-source on -k "regex:${NCU_KERNEL}" -c ${NCU_COUNT:-2} -f -o $OUT/${TAG}_kernel \
+		${NCU_CMD:-python benchmarks/configs.py --only cfg5 --no-reference --repeats 1} > $OUT/${TAG}_ncu_kernel.log 2>&1
+	ls -la $OUT/${TAG}_kernel.ncu-rep ;;
 probe)
 	timeout 900 python benchmarks/patched_probe.py --out $OUT/${TAG}_patched_probe.json 2>&1 | tee $OUT/${TAG}_patched_probe.txt ;;
 configs)
