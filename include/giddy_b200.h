@@ -24,7 +24,7 @@
  *      cites the reference __global__ function it replaces.
  *
  *  (3) Fused composite decoders, (4) host-resident scans, (5) shard planning, (6) host memory placement,
- *      (7) device groups, (8) compressors: see the section comments below.
+ *      (7) device groups, (8) compressors, (9) utility kernels: see the section comments below.
  *
  * Conventions: every function returns a giddy_status_t (0 = success) unless it
  * returns a pointer/count; on failure giddy_last_error() holds a message for the
@@ -662,6 +662,37 @@ GIDDY_API giddy_status_t giddy_b200_incidence_bitmaps_compress_launch(
 	void* stream, const giddy_launch_config_t* config, unsigned uncompressed_size, unsigned bitmap_alignment_in_ints, int use_dictionary,
 	void* bitmaps, const void* uncompressed, const void* dictionary_entries, uint64_t length, unsigned num_bitmaps,
 	unsigned* status_flags);
+
+/* ------------------------------------------------------------------------- */
+/* (9) Utility kernels which the reference has but neither wraps nor registers */
+/* (SURVEY.md 8f-4).                                                           */
+/* ------------------------------------------------------------------------- */
+
+/* decompression::model::decompress_with_intervals<IndexSize, Uncompressed, UnaryModelFunction>
+ * src/kernels/decompression/model.cuh:55-98.  decompressed[i] = model_s(i - s * modeling_period), s = i / modeling_period;
+ * coefficients of the uncompressed (signed) type, 1 (constant) or 2 (linear) per interval.  The reference's derived parameter
+ * intervals_per_block is not needed. */
+GIDDY_API const void* giddy_b200_model_with_intervals_kernel(unsigned index_size, unsigned uncompressed_size, giddy_model_t model);
+GIDDY_API giddy_status_t giddy_b200_model_with_intervals_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned index_size, unsigned uncompressed_size, giddy_model_t model,
+	void* decompressed, const void* interval_model_coefficients, uint64_t modeling_period, uint64_t length);
+
+/* gather::gather<OutputIndexSize, ElementSize, InputIndexSize>, src/kernels/data_layout/gather.cuh:151-164:
+ * reordered_data[i] = data[indices[i]], i < num_indices.  The kernel behind dictionary::decompress, under its own name. */
+GIDDY_API const void* giddy_b200_gather_kernel(unsigned output_index_size, unsigned element_size, unsigned input_index_size);
+GIDDY_API giddy_status_t giddy_b200_gather_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned output_index_size, unsigned element_size, unsigned input_index_size,
+	void* reordered_data, const void* data, const void* indices, uint64_t data_length, uint64_t num_indices,
+	int cache_data_in_shared_memory, unsigned serialization_factor);
+
+/* Inclusive prefix sum with ReductionOp = plus: result[i] = *initial_value + data[0] + ... + data[i] (mod 2^(8 result_size)); the
+ * job of the reference's reduce_segments + scan_using_segment_reductions (src/kernels/reduction/scan.cuh:127, 412) or
+ * scan_single_segment (:525), in one launch and one pass (tiles with decoupled look-back).  initial_value: a device pointer to one
+ * element of the result type, or NULL for zero.  Sizes: those of delta::decompress. */
+GIDDY_API const void* giddy_b200_inclusive_scan_kernel(unsigned index_size, unsigned result_size, unsigned input_size);
+GIDDY_API giddy_status_t giddy_b200_inclusive_scan_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned index_size, unsigned result_size, unsigned input_size,
+	void* result, const void* data, uint64_t length, const void* initial_value);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -2,6 +2,7 @@
 // Instantiations: src/kernel_wrappers/decompression/delta.cu:94-106.
 #include "abi_internal.hpp"
 #include "../kernels/delta.cuh"
+#include <vector>
 
 using namespace giddy;
 using namespace giddy::abi;
@@ -19,13 +20,26 @@ giddy_status_t delta_launch(void* stream, const giddy_launch_config_t* cfg, void
 		static_cast<uint_t<U>*>(out), static_cast<const uint_t<C>*>(in), static_cast<const uint_t<U>*>(anchors),
 		(size_type<I>) n, (size_type<I>) L);
 }
-// Whether grids can be launched cooperatively on the current device (all CTAs resident at once).
-bool cooperative_launch_supported()
+// How many CTAs of `block` threads of `kernel` fit the current device at once, if grids can be launched cooperatively there
+// (0 if not).  Asked of the runtime once per (device, kernel, block size) and thread.
+unsigned resident_blocks(const void* kernel, unsigned block)
 {
-	int device = 0, supported = 0;
-	if (cudaGetDevice(&device) != cudaSuccess) { return false; }
-	if (cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, device) != cudaSuccess) { return false; }
-	return supported != 0;
+	struct key_t { int device; const void* kernel; unsigned block; };
+	struct entry_t { key_t key; unsigned resident; };
+	static thread_local ::std::vector<entry_t> known;
+	int device = 0;
+	if (cudaGetDevice(&device) != cudaSuccess) { return 0; }
+	for (const auto& e : known) { if (e.key.device == device && e.key.kernel == kernel && e.key.block == block) { return e.resident; } }
+	int supported = 0, multiprocessors = 0, per_multiprocessor = 0;
+	unsigned resident = 0;
+	if (cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, device) == cudaSuccess && supported != 0 &&
+		cudaDeviceGetAttribute(&multiprocessors, cudaDevAttrMultiProcessorCount, device) == cudaSuccess &&
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_multiprocessor, kernel, (int) block, 0) == cudaSuccess) {
+		resident = (unsigned) multiprocessors * (unsigned) per_multiprocessor;
+	}
+	else { cudaGetLastError(); }
+	known.push_back({ { device, kernel, block }, resident });
+	return resident;
 }
 
 template <unsigned I, unsigned U, unsigned C>
@@ -36,25 +50,19 @@ giddy_status_t delta_long_launch(void* stream, const giddy_launch_config_t* cfg,
 	auto in_ = static_cast<const uint_t<C>*>(in);
 	auto anchors_ = static_cast<const uint_t<U>*>(anchors);
 	size_type<I> n_ = (size_type<I>) n, L_ = (size_type<I>) L;
-	if (cooperative_launch_supported()) {
-		// statically assigned tiles: every CTA must be resident, which a cooperative launch of at most
-		// (CTAs per multiprocessor) x (multiprocessors) CTAs guarantees
-		auto kernel = kernels::delta_decompress_long_segments<I, U, C, true>;
-		int device = 0, multiprocessors = 0, per_multiprocessor = 0;
-		cudaError_t error = cudaGetDevice(&device);
-		if (error == cudaSuccess) { error = cudaDeviceGetAttribute(&multiprocessors, cudaDevAttrMultiProcessorCount, device); }
-		const unsigned block = cfg->block_dimensions[0];
-		if (error == cudaSuccess) { error = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_multiprocessor, kernel, (int) block, 0); }
-		if (error != cudaSuccess) { return fail_cuda(error, "occupancy query (Delta look-back)"); }
-		const unsigned resident = (unsigned) multiprocessors * (unsigned) per_multiprocessor;
-		if (resident > 0) {
-			const unsigned grid = cfg->grid_dimensions[0] < resident ? cfg->grid_dimensions[0] : resident;
-			void* arguments[] = { &out_, &in_, &anchors_, &n_, &L_, &workspace };
-			error = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(block), arguments, 0,
-				static_cast<cudaStream_t>(stream));
-			if (error != cudaSuccess) { return fail_cuda(error, "cooperative kernel launch (Delta look-back)"); }
-			return GIDDY_SUCCESS;
-		}
+	// statically assigned tiles: every CTA must be resident, which a cooperative launch of at most
+	// (CTAs per multiprocessor) x (multiprocessors) CTAs guarantees
+	const void* kernel = reinterpret_cast<const void*>(&kernels::delta_decompress_long_segments<I, U, C, true>);
+	const unsigned block = cfg->block_dimensions[0];
+	const unsigned resident = resident_blocks(kernel, block);
+	if (resident > 0) {
+		const unsigned grid = cfg->grid_dimensions[0] < resident ? cfg->grid_dimensions[0] : resident;
+		void* arguments[] = { &out_, &in_, &anchors_, &n_, &L_, &workspace };
+		const cudaError_t error = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(block), arguments, 0, static_cast<cudaStream_t>(stream));
+		if (error == cudaSuccess) { return GIDDY_SUCCESS; }
+		// (MPS / green-context SM limits can refuse a cooperative grid which the occupancy query allowed: fall back to the
+		// ticket-counter kernel, which is correct under any residency)
+		cudaGetLastError();
 	}
 	return launch(kernels::delta_decompress_long_segments<I, U, C, false>, stream, cfg, out_, in_, anchors_, n_, L_, workspace);
 }
@@ -115,4 +123,31 @@ extern "C" giddy_status_t giddy_b200_delta_launch(
 	error = cudaFreeAsync(workspace, s);
 	if (status == GIDDY_SUCCESS && error != cudaSuccess) { return fail_cuda(error, "cudaFreeAsync (Delta look-back workspace)"); }
 	return status;
+}
+
+
+// ---- Inclusive prefix sums (reference src/kernels/reduction/scan.cuh: reduce_segments :127 + scan_using_segment_reductions
+// :412, or scan_single_segment :525 -- kernels the reference has but does not wrap) -----------------------------------------
+// A prefix sum is a Delta column with a single segment whose anchor is the initial value: one launch of the look-back
+// kernel (one pass over the data) where the reference needs two kernels and two passes, or a single block.
+
+namespace { __device__ unsigned long long giddy_scan_zero_anchor[1] = { 0ull }; }
+
+extern "C" const void* giddy_b200_inclusive_scan_kernel(unsigned I, unsigned result_size, unsigned input_size)
+{
+	return giddy_b200_delta_kernel(I, result_size, input_size);
+}
+
+extern "C" giddy_status_t giddy_b200_inclusive_scan_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned I, unsigned result_size, unsigned input_size,
+	void* result, const void* data, uint64_t length, const void* initial_value)
+{
+	if (initial_value == nullptr) { // a zero of the library's own, on the current device
+		void* zero = nullptr;
+		cudaError_t error = cudaGetSymbolAddress(&zero, giddy_scan_zero_anchor);
+		if (error != cudaSuccess) { return fail_cuda(error, "cudaGetSymbolAddress (scan initial value)"); }
+		initial_value = zero;
+	}
+	if (length == 0) { return GIDDY_SUCCESS; }
+	return giddy_b200_delta_launch(stream, config, I, result_size, input_size, result, data, initial_value, length, length);
 }

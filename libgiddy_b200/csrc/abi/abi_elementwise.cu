@@ -193,3 +193,62 @@ extern "C" giddy_status_t giddy_b200_dictionary_launch(
 	return e->launch(stream, config, decompressed, compressed_input, dictionary_entries, length, num_dictionary_entries,
 		cache_dictionary_in_shared_memory != 0, (unsigned short) serialization_factor);
 }
+
+// ---- Utility kernels the reference has but does not wrap --------------------------------------------
+
+namespace {
+
+using intervals_launcher_t = giddy_status_t (*)(void*, const giddy_launch_config_t*, void*, const void*, uint64_t, uint64_t);
+struct intervals_entry_t { unsigned I, U; int model; const void* kernel; intervals_launcher_t launch; };
+template <unsigned I, unsigned U, int M>
+giddy_status_t intervals_launch(void* stream, const giddy_launch_config_t* cfg, void* out, const void* coeffs, uint64_t period, uint64_t n)
+{
+	return launch(kernels::model_decompress_with_intervals<I, U, M>, stream, cfg, static_cast<uint_t<U>*>(out), static_cast<const int_t<U>*>(coeffs),
+		(size_type<I>) period, (size_type<I>) n);
+}
+#define INTERVALS_ENTRY(I, U, M) { I, U, M, reinterpret_cast<const void*>(&kernels::model_decompress_with_intervals<I, U, M>), &intervals_launch<I, U, M> }
+const intervals_entry_t intervals_table[] = {
+	INTERVALS_ENTRY(4, 2, model_linear), INTERVALS_ENTRY(4, 4, model_linear), INTERVALS_ENTRY(8, 4, model_linear),
+	INTERVALS_ENTRY(4, 2, model_constant), INTERVALS_ENTRY(4, 4, model_constant),
+};
+const intervals_entry_t* find_intervals(unsigned I, unsigned U, int model)
+{
+	for (const auto& e : intervals_table) { if (e.I == I && e.U == U && e.model == model) { return &e; } }
+	return nullptr;
+}
+
+} // namespace
+
+extern "C" const void* giddy_b200_model_with_intervals_kernel(unsigned I, unsigned U, giddy_model_t model)
+{
+	auto e = find_intervals(I, U, (int) model);
+	return e ? e->kernel : nullptr;
+}
+
+extern "C" giddy_status_t giddy_b200_model_with_intervals_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned I, unsigned U, giddy_model_t model,
+	void* decompressed, const void* interval_model_coefficients, uint64_t modeling_period, uint64_t length)
+{
+	auto e = find_intervals(I, U, (int) model);
+	giddy_status_t status;
+	if (!check_launch(config, e ? e->kernel : nullptr, status)) { return status; }
+	if (modeling_period == 0) { return fail(GIDDY_INVALID_ARGUMENT, "The modeling period must be a positive number"); }
+	if (length == 0) { return GIDDY_SUCCESS; }
+	return e->launch(stream, config, decompressed, interval_model_coefficients, modeling_period, length);
+}
+
+// gather<OutputIndexSize, ElementSize, InputIndexSize> (reference src/kernels/data_layout/gather.cuh:151-164) is the kernel
+// behind dictionary::decompress (dictionary.cuh:61-75 calls gather::detail::gather): the same launcher under its own name.
+extern "C" const void* giddy_b200_gather_kernel(unsigned output_index_size, unsigned element_size, unsigned input_index_size)
+{
+	return giddy_b200_dictionary_kernel(output_index_size, element_size, input_index_size);
+}
+
+extern "C" giddy_status_t giddy_b200_gather_launch(
+	void* stream, const giddy_launch_config_t* config, unsigned output_index_size, unsigned element_size, unsigned input_index_size,
+	void* reordered_data, const void* data, const void* indices, uint64_t data_length, uint64_t num_indices,
+	int cache_data_in_shared_memory, unsigned serialization_factor)
+{
+	return giddy_b200_dictionary_launch(stream, config, output_index_size, element_size, input_index_size, reordered_data, indices, data,
+		num_indices, data_length, cache_data_in_shared_memory, serialization_factor);
+}

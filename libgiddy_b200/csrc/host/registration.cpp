@@ -2,6 +2,7 @@
 // the same set, under the same keys, as the reference registers in the static_block of each of its
 // src/kernel_wrappers/**/*.cu files (cited per group; full key list: SURVEY.md Appendix C).
 #include "kernel_wrappers.hpp"
+#include "compression_wrappers.hpp"
 
 #include <mutex>
 
@@ -141,6 +142,96 @@ void register_all_wrappers()
 		kernel_t<4, int16_t, int8_t,  models::constant<4, int32_t>, 4>::registerInSubclassFactory();
 		kernel_t<4, int32_t, int8_t,  models::constant<4, int32_t>, 4>::registerInSubclassFactory();
 		kernel_t<4, int32_t, int16_t, models::constant<4, int32_t>, 4>::registerInSubclassFactory();
+	}
+	// Extensions (no reference counterpart: "compression ... is not included", README.md:128-130): the compressors, under the
+	// decompressors' type tuples
+	{
+		using namespace compression::frame_of_reference;
+		kernel_t<4, int16_t, int8_t,  models::linear  <4, int32_t>>::registerInSubclassFactory();
+		kernel_t<4, int32_t, int8_t,  models::linear  <4, int32_t>>::registerInSubclassFactory();
+		kernel_t<4, int32_t, int16_t, models::linear  <4, int32_t>>::registerInSubclassFactory();
+		kernel_t<8, int32_t, int16_t, models::linear  <4, int32_t>>::registerInSubclassFactory();
+		kernel_t<4, int16_t, int8_t,  models::constant<4, int32_t>>::registerInSubclassFactory();
+		kernel_t<4, int32_t, int8_t,  models::constant<4, int32_t>>::registerInSubclassFactory();
+		kernel_t<4, int32_t, int16_t, models::constant<4, int32_t>>::registerInSubclassFactory();
+	}
+#define GIDDY_REGISTER_UC_PAIRS(I) \
+	kernel_t<I, 2, 1>::registerInSubclassFactory(); kernel_t<I, 4, 1>::registerInSubclassFactory(); \
+	kernel_t<I, 4, 2>::registerInSubclassFactory(); kernel_t<I, 8, 1>::registerInSubclassFactory(); \
+	kernel_t<I, 8, 2>::registerInSubclassFactory(); kernel_t<I, 8, 4>::registerInSubclassFactory();
+	{ using namespace compression::delta; GIDDY_REGISTER_UC_PAIRS(4) GIDDY_REGISTER_UC_PAIRS(8) }
+	{ using namespace compression::discard_zero_bytes::fixed_width; GIDDY_REGISTER_UC_PAIRS(4) GIDDY_REGISTER_UC_PAIRS(8) }
+#undef GIDDY_REGISTER_UC_PAIRS
+	{
+		using namespace compression::dictionary;
+#define GIDDY_REGISTER_DICTIONARY(I) \
+		kernel_t<I, 1, 1>::registerInSubclassFactory(); kernel_t<I, 2, 1>::registerInSubclassFactory(); kernel_t<I, 2, 2>::registerInSubclassFactory(); \
+		kernel_t<I, 4, 1>::registerInSubclassFactory(); kernel_t<I, 4, 2>::registerInSubclassFactory(); kernel_t<I, 4, 4>::registerInSubclassFactory(); \
+		kernel_t<I, 8, 1>::registerInSubclassFactory(); kernel_t<I, 8, 2>::registerInSubclassFactory(); kernel_t<I, 8, 4>::registerInSubclassFactory(); \
+		kernel_t<I, 8, 8>::registerInSubclassFactory();
+		GIDDY_REGISTER_DICTIONARY(4) GIDDY_REGISTER_DICTIONARY(8)
+#undef GIDDY_REGISTER_DICTIONARY
+	}
+	{
+		using namespace compression::run_length_encoding;
+		kernel_t<4, 1, 1>::registerInSubclassFactory(); kernel_t<4, 2, 1>::registerInSubclassFactory();
+		kernel_t<4, 4, 1>::registerInSubclassFactory(); kernel_t<4, 8, 1>::registerInSubclassFactory();
+		kernel_t<4, 1, 2>::registerInSubclassFactory(); kernel_t<4, 2, 2>::registerInSubclassFactory();
+		kernel_t<4, 4, 2>::registerInSubclassFactory(); kernel_t<4, 8, 2>::registerInSubclassFactory();
+		kernel_t<4, 1, 4>::registerInSubclassFactory(); kernel_t<4, 2, 4>::registerInSubclassFactory();
+		kernel_t<4, 4, 4>::registerInSubclassFactory(); kernel_t<4, 8, 4>::registerInSubclassFactory();
+		kernel_t<8, 4, 1>::registerInSubclassFactory(); kernel_t<8, 4, 2>::registerInSubclassFactory();
+		kernel_t<8, 4, 4>::registerInSubclassFactory();
+		kernel_t<8, 1, 8>::registerInSubclassFactory(); kernel_t<8, 4, 8>::registerInSubclassFactory();
+		kernel_t<8, 8, 8>::registerInSubclassFactory();
+	}
+	{
+		using namespace compression::run_position_encoding;
+		kernel_t<4, 1, 2, true>::registerInSubclassFactory();  kernel_t<4, 2, 2, true>::registerInSubclassFactory();
+		kernel_t<4, 4, 2, true>::registerInSubclassFactory();  kernel_t<4, 8, 2, true>::registerInSubclassFactory();
+		kernel_t<8, 4, 2, true>::registerInSubclassFactory();
+		kernel_t<4, 1, 4, false>::registerInSubclassFactory(); kernel_t<4, 2, 4, false>::registerInSubclassFactory();
+		kernel_t<4, 4, 4, false>::registerInSubclassFactory(); kernel_t<4, 8, 4, false>::registerInSubclassFactory();
+		kernel_t<8, 4, 8, false>::registerInSubclassFactory();
+	}
+	{
+		using namespace compression::discard_zero_bytes::variable_width;
+		kernel_t<4, 2, 4>::registerInSubclassFactory(); kernel_t<4, 4, 4>::registerInSubclassFactory(); kernel_t<4, 8, 4>::registerInSubclassFactory();
+		kernel_t<8, 2, 4>::registerInSubclassFactory(); kernel_t<8, 4, 4>::registerInSubclassFactory(); kernel_t<8, 8, 4>::registerInSubclassFactory();
+		kernel_t<4, 2, 8>::registerInSubclassFactory(); kernel_t<4, 4, 8>::registerInSubclassFactory(); kernel_t<4, 8, 8>::registerInSubclassFactory();
+	}
+	{
+		using namespace compression::incidence_bitmaps;
+		kernel_t<4, 1, 2, true>::registerInSubclassFactory(); kernel_t<4, 2, 2, true>::registerInSubclassFactory();
+		kernel_t<4, 4, 2, true>::registerInSubclassFactory(); kernel_t<4, 8, 2, true>::registerInSubclassFactory();
+		kernel_t<4, 1, 2, false>::registerInSubclassFactory();
+	}
+	// Utility kernels which the reference has but does not register
+	{
+		using namespace cuda::kernels::gather;
+#define GIDDY_REGISTER_GATHER(I) \
+		kernel_t<I, 1, 1>::registerInSubclassFactory(); kernel_t<I, 2, 1>::registerInSubclassFactory(); kernel_t<I, 2, 2>::registerInSubclassFactory(); \
+		kernel_t<I, 4, 1>::registerInSubclassFactory(); kernel_t<I, 4, 2>::registerInSubclassFactory(); kernel_t<I, 4, 4>::registerInSubclassFactory(); \
+		kernel_t<I, 8, 1>::registerInSubclassFactory(); kernel_t<I, 8, 2>::registerInSubclassFactory(); kernel_t<I, 8, 4>::registerInSubclassFactory(); \
+		kernel_t<I, 8, 8>::registerInSubclassFactory();
+		GIDDY_REGISTER_GATHER(4) GIDDY_REGISTER_GATHER(8)
+#undef GIDDY_REGISTER_GATHER
+	}
+	{
+		using namespace decompression::model::intervals;
+		kernel_t<4, int16_t, models::linear  <4, int16_t>>::registerInSubclassFactory();
+		kernel_t<4, int32_t, models::linear  <4, int32_t>>::registerInSubclassFactory();
+		kernel_t<8, int32_t, models::linear  <8, int32_t>>::registerInSubclassFactory();
+		kernel_t<4, int16_t, models::constant<4, int16_t>>::registerInSubclassFactory();
+		kernel_t<4, int32_t, models::constant<4, int32_t>>::registerInSubclassFactory();
+	}
+	{
+		using namespace cuda::kernels::reduction::scan;
+#define GIDDY_REGISTER_SCAN(I) \
+		kernel_t<I, 2, 1>::registerInSubclassFactory(); kernel_t<I, 4, 1>::registerInSubclassFactory(); kernel_t<I, 4, 2>::registerInSubclassFactory(); \
+		kernel_t<I, 8, 1>::registerInSubclassFactory(); kernel_t<I, 8, 2>::registerInSubclassFactory(); kernel_t<I, 8, 4>::registerInSubclassFactory();
+		GIDDY_REGISTER_SCAN(4) GIDDY_REGISTER_SCAN(8)
+#undef GIDDY_REGISTER_SCAN
 	}
 }
 

@@ -203,6 +203,68 @@ __global__ void model_decompress(
 }
 
 // -------------------------------------------------------------------------------------------------
+// Model with intervals.  Replaces cuda::kernels::decompression::model::decompress_with_intervals, reference
+// src/kernels/decompression/model.cuh:55-98 (a kernel the reference has but never wraps or registers):
+//   decompressed[i] = (U) model_s(i - s * modeling_period),  s = i / modeling_period
+// -- Frame of Reference without the offsets.  Coefficients are of the uncompressed type, `dim` per interval.
+// -------------------------------------------------------------------------------------------------
+template <unsigned IndexSize, unsigned U, int Model>
+__global__ void model_decompress_with_intervals(
+	uint_t<U>*        __restrict__  decompressed,
+	const int_t<U>*   __restrict__  interval_model_coefficients,
+	size_type<IndexSize>            modeling_period,
+	size_type<IndexSize>            length)
+{
+	using size_t_ = size_type<IndexSize>;
+	constexpr unsigned E = 16 / U;
+	constexpr unsigned dim = (Model == model_linear) ? 2 : 1;
+	constexpr unsigned unroll = detail::elementwise_unroll;
+	const detail::segment_locator<size_t_> locator(modeling_period);
+	const uint64_t global_thread = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	auto value_at = [&](size_t_ position) {
+		size_t_ s, x;
+		locator.locate(position, s, x);
+		int_t<U> c[dim];
+		#pragma unroll
+		for (unsigned d = 0; d < dim; d++) { c[d] = __ldg(interval_model_coefficients + (size_t) s * dim + d); }
+		return detail::evaluate_model<Model, IndexSize, int_t<U>, U>(c, x);
+	};
+	if (!is_aligned_to(decompressed, 16)) {
+		for (uint64_t p = global_thread; p < length; p += (uint64_t) gridDim.x * blockDim.x) { decompressed[p] = value_at((size_t_) p); }
+		return;
+	}
+	const uint64_t num_vectors = length / E;
+	const uint64_t vectors_per_tile = (uint64_t) blockDim.x * unroll;
+	#pragma unroll 1
+	for (uint64_t tile_start = (uint64_t) blockIdx.x * vectors_per_tile; tile_start < num_vectors; tile_start += (uint64_t) gridDim.x * vectors_per_tile) {
+		#pragma unroll
+		for (unsigned k = 0; k < unroll; k++) {
+			const uint64_t v = tile_start + (uint64_t) k * blockDim.x + threadIdx.x;
+			if (v >= num_vectors) { continue; }
+			size_t_ s, x;
+			locator.locate((size_t_)(v * E), s, x);
+			int_t<U> c[dim];
+			#pragma unroll
+			for (unsigned d = 0; d < dim; d++) { c[d] = __ldg(interval_model_coefficients + (size_t) s * dim + d); }
+			byte_pack<16> out;
+			#pragma unroll
+			for (unsigned j = 0; j < E; j++) {
+				out.template set<U>(j, detail::evaluate_model<Model, IndexSize, int_t<U>, U>(c, x));
+				x++;
+				if (x == modeling_period && j + 1 < E) { // the vector straddles an interval boundary
+					x = 0; s++;
+					#pragma unroll
+					for (unsigned d = 0; d < dim; d++) { c[d] = __ldg(interval_model_coefficients + (size_t) s * dim + d); }
+				}
+			}
+			store_pack_16(decompressed + v * E, out);
+		}
+	}
+	const uint64_t tail_position = num_vectors * E + global_thread;
+	if (tail_position < length) { decompressed[tail_position] = value_at((size_t_) tail_position); }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Discard zero bytes, fixed width.  Replaces
 // cuda::kernels::decompression::discard_zero_bytes::fixed_width::decompress,
 // reference src/kernels/decompression/discard_zero_bytes_fixed.cuh:108-124 (little-endian):

@@ -393,3 +393,59 @@ def compressed_indices_scatter(target, data_to_scatter, run_lengths, run_individ
                  "anchoring_period": ii(anchoring_period), "num_scatter_position_runs": ii(num_runs),
                  "input_data_length": N.size_type_by_index_size(input_index_size)(input_data_length)},
                 stream, limits)
+
+
+# ---- utility kernels which the reference has but does not register (include/giddy_b200.h group 9) --------------------------
+
+def gather_key(output_index_size, element_size, input_index_size):
+    return "gather::kernel_t<%du, %du, %du>" % (output_index_size, element_size, input_index_size)
+
+
+def gather(reordered_data, data, indices, data_length, num_indices, *, element_size, input_index_size, output_index_size=4,
+           cache_in_shared_memory=None, stream=None, limits=None, library=None):
+    """reference kernel: src/kernels/data_layout/gather.cuh:151-164.  reordered_data[i] = data[indices[i]]"""
+    _check_size(reordered_data, element_size, "reordered_data")
+    _check_size(indices, input_index_size, "indices")
+    resolve = {"data_length": N.size_t(data_length), "num_indices": N.size_t(num_indices)}
+    if cache_in_shared_memory is not None:
+        resolve["cache_input_data_in_shared_mem"] = N.boolean(cache_in_shared_memory)
+    return _run(library, gather_key(output_index_size, element_size, input_index_size), resolve,
+                {"reordered_data": N.ptr(reordered_data, _UTAG[element_size]), "data": N.cptr(data, _UTAG[element_size]),
+                 "indices": N.cptr(indices, _UTAG[input_index_size]),
+                 "data_length": N.size_type_by_index_size(input_index_size)(data_length),
+                 "num_indices": N.size_type_by_index_size(output_index_size)(num_indices)},
+                stream, limits)
+
+
+def model_with_intervals_key(index_size, uncompressed_size, model="linear"):
+    return "decompression::model::intervals::kernel_t<%du, %s, %s >" % (
+        index_size, _SIGNED_NAMES[uncompressed_size], model_type_name(model, index_size, uncompressed_size))
+
+
+def model_with_intervals(decompressed, interval_model_coefficients, modeling_period, length, *, uncompressed_size, model="linear", index_size=4,
+                         stream=None, limits=None, library=None):
+    """reference kernel: src/kernels/decompression/model.cuh:55-98.  decompressed[i] = model_s(i - s * modeling_period)"""
+    _check_size(decompressed, uncompressed_size, "decompressed")
+    dim = 2 if model == "linear" else 1
+    index = N.uint_of_size(index_size)
+    return _run(library, model_with_intervals_key(index_size, uncompressed_size, model),
+                {"length": N.size_t(length), "modeling_period": N.size_t(modeling_period)},
+                {"decompressed": N.ptr(decompressed, _ITAG[uncompressed_size]),
+                 "interval_model_coefficients": N.cptr(interval_model_coefficients, "array_%s_%d" % (_ITAG[uncompressed_size], dim)),
+                 "modeling_period": index(modeling_period), "length": index(length)},
+                stream, limits)
+
+
+def inclusive_scan_key(index_size, result_size, input_size):
+    return "reduction::scan::inclusive::plus::kernel_t<%du, %du, %du>" % (index_size, result_size, input_size)
+
+
+def inclusive_scan(result, data, length, *, result_size, input_size, initial_value=None, index_size=4, stream=None, limits=None, library=None):
+    """result[i] = initial + data[0] + ... + data[i]: the reference's scan kernels (src/kernels/reduction/scan.cuh:127, 412, 525) in one pass.
+    initial_value: a one-element device tensor of the result type, or None for zero."""
+    _check_size(result, result_size, "result")
+    _check_size(data, input_size, "data")
+    arguments = {"result": N.ptr(result, _UTAG[result_size]), "data": N.cptr(data, _UTAG[input_size]), "length": N.uint_of_size(index_size)(length)}
+    if initial_value is not None:
+        arguments["initial_value"] = N.cptr(initial_value, _UTAG[result_size])
+    return _run(library, inclusive_scan_key(index_size, result_size, input_size), {"length": N.size_t(length)}, arguments, stream, limits)
