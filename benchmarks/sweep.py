@@ -36,6 +36,9 @@ def workloads(log2_n):
     w.append(("RLE u32 run16 L=4096", lambda: cases.rle_case(1, n, 4096, 4, 2)))
     w.append(("RLE u64 run64 L=1024", lambda: cases.rle_case(1, n // 2, 1024, 8, 2, mean_run=64)))
     w.append(("RLE u8 run16 L=1024", lambda: cases.rle_case(1, n, 1024, 1, 1)))
+    w.append(("RLE u16 run16 L=1024", lambda: cases.rle_case(1, n, 1024, 2, 2)))
+    w.append(("RPE u16 abs run16 L=1024", lambda: cases.rpe_case(1, n, 1024, 2, 4, False)))
+    w.append(("RPE u8 abs run16 L=1024", lambda: cases.rpe_case(1, n, 1024, 1, 4, False)))
     w.append(("cfg5 RPE u32 abs run64 L=1024", lambda: cases.rpe_case(1, n, 1024, 4, 4, False, mean_run=64)))
     w.append(("RPE u32 rel run16 L=1024", lambda: cases.rpe_case(1, n, 1024, 4, 2, True, avoid_boundary_runs=True)))
     w.append(("cfg4 Delta u64<-u32 L=1024", lambda: cases.delta_case(1, n // 2, 1024, 8, 4)))

@@ -52,6 +52,8 @@ probe)
 	timeout 900 python benchmarks/patched_probe.py --out $OUT/${TAG}_patched_probe.json 2>&1 | tee $OUT/${TAG}_patched_probe.txt ;;
 configs)
 	timeout 1500 python benchmarks/configs.py --out $OUT/${TAG}_configs.json 2>&1 | tee $OUT/${TAG}_configs.txt ;;
+compress)
+	timeout 900 python benchmarks/compress_sweep.py --out $OUT/${TAG}_compress_sweep.json 2>&1 | tee $OUT/${TAG}_compress_sweep.txt ;;
 sweep)
 	timeout 1500 python benchmarks/sweep.py --log2-n 27 --out $OUT/${TAG}_sweep.json 2>&1 | tee $OUT/${TAG}_sweep.txt | tail -70 ;;
 ncu_patched)
