@@ -110,12 +110,16 @@ struct run_plan_t {
 	uint64_t* placement;       // num_tiles + 1
 	uint64_t* open_run_start;  // num_tiles
 	uint64_t* starts;          // run_capacity + 1
+	uint64_t num_chunks;       // chunks of 1024 tiles
+	uint64_t* chunk_open;      // num_chunks: the chunks' last natural heads, then their exclusive scan
+	uint64_t* chunk_totals;    // num_chunks + 1: the chunks' run counts, then their exclusive scan; [num_chunks] = the number of runs
 };
 
 size_t run_workspace_bytes(uint64_t n, uint64_t run_capacity, run_plan_t& plan)
 {
 	plan.num_tiles = (n + enc::run_tile_elements - 1) / enc::run_tile_elements;
-	return plan.num_tiles * sizeof(enc::run_tile_summary_t) + (plan.num_tiles + 1) * 8 + plan.num_tiles * 8 + (run_capacity + 1) * 8 + 64;
+	plan.num_chunks = (plan.num_tiles + enc::placement_chunk_tiles - 1) / enc::placement_chunk_tiles;
+	return plan.num_tiles * sizeof(enc::run_tile_summary_t) + (plan.num_tiles + 1) * 8 + plan.num_tiles * 8 + (run_capacity + 1) * 8 + (2 * plan.num_chunks + 1) * 8 + 64;
 }
 
 void run_workspace_layout(void* memory, uint64_t run_capacity, run_plan_t& plan)
@@ -124,8 +128,9 @@ void run_workspace_layout(void* memory, uint64_t run_capacity, run_plan_t& plan)
 	plan.summaries = reinterpret_cast<enc::run_tile_summary_t*>(p); p += plan.num_tiles * sizeof(enc::run_tile_summary_t);
 	plan.placement = reinterpret_cast<uint64_t*>(p); p += (plan.num_tiles + 1) * 8;
 	plan.open_run_start = reinterpret_cast<uint64_t*>(p); p += plan.num_tiles * 8;
-	plan.starts = reinterpret_cast<uint64_t*>(p);
-	(void) run_capacity;
+	plan.starts = reinterpret_cast<uint64_t*>(p); p += (run_capacity + 1) * 8;
+	plan.chunk_open = reinterpret_cast<uint64_t*>(p); p += plan.num_chunks * 8;
+	plan.chunk_totals = reinterpret_cast<uint64_t*>(p);
 }
 
 template <unsigned U>
@@ -133,13 +138,29 @@ giddy_status_t run_common(cudaStream_t s, const giddy_launch_config_t* cfg, cons
 	uint64_t max_run_length, uint64_t run_capacity, unsigned* status)
 {
 	const unsigned blocks = cfg->grid_dimensions[0] ? cfg->grid_dimensions[0] : helper_blocks(plan.num_tiles, 1);
-	enc::run_tile_summaries<U><<<blocks, enc::run_tile_threads, 0, s>>>(plan.summaries, static_cast<const uint_t<U>*>(in), n, max_run_length);
+	auto x = static_cast<const uint_t<U>*>(in);
+	// runs limited to at least a tile's length (or not at all) have at most one split point per tile: the mask-based kernels
+	const bool fast = max_run_length == 0 || max_run_length >= enc::run_tile_elements;
+	if (fast) { enc::run_tile_summaries_fast<U><<<blocks, enc::run_tile_threads, 0, s>>>(plan.summaries, x, n); }
+	else { enc::run_tile_summaries<U><<<blocks, enc::run_tile_threads, 0, s>>>(plan.summaries, x, n, max_run_length); }
 	giddy_status_t result = launched("kernel launch (run tile summaries)");
 	if (result != GIDDY_SUCCESS) { return result; }
-	enc::run_tile_placement<<<1, 1024, 0, s>>>(plan.placement, plan.open_run_start, plan.summaries, plan.num_tiles, n, max_run_length);
+	const unsigned chunks = (unsigned) plan.num_chunks;
+	enc::run_chunk_last_heads<<<chunks, enc::placement_chunk_tiles, 0, s>>>(plan.chunk_open, plan.summaries, plan.num_tiles);
+	enc::run_scan_chunks<true><<<1, 1024, 0, s>>>(plan.chunk_open, plan.num_chunks, nullptr);
+	enc::run_tile_counts<<<chunks, enc::placement_chunk_tiles, 0, s>>>(plan.placement, plan.open_run_start, plan.chunk_totals, plan.chunk_open, plan.summaries,
+		plan.num_tiles, n, max_run_length);
+	enc::run_scan_chunks<false><<<1, 1024, 0, s>>>(plan.chunk_totals, plan.num_chunks, plan.chunk_totals + plan.num_chunks);
+	enc::run_tile_places<<<chunks, enc::placement_chunk_tiles, 0, s>>>(plan.placement, plan.chunk_totals, plan.chunk_totals + plan.num_chunks, plan.num_tiles);
 	if ((result = launched("kernel launch (run tile placement)")) != GIDDY_SUCCESS) { return result; }
-	enc::run_emit<U, uint64_t><<<blocks, enc::run_tile_threads, 0, s>>>(static_cast<uint_t<U>*>(run_data), plan.starts, static_cast<const uint_t<U>*>(in),
-		plan.placement, plan.open_run_start, n, max_run_length, run_capacity, status);
+	if (fast) {
+		enc::run_emit_fast<U, uint64_t><<<blocks, enc::run_tile_threads, 0, s>>>(static_cast<uint_t<U>*>(run_data), plan.starts, x,
+			plan.placement, plan.open_run_start, plan.summaries, n, max_run_length, run_capacity, status);
+	}
+	else {
+		enc::run_emit<U, uint64_t><<<blocks, enc::run_tile_threads, 0, s>>>(static_cast<uint_t<U>*>(run_data), plan.starts, x,
+			plan.placement, plan.open_run_start, n, max_run_length, run_capacity, status);
+	}
 	return launched("kernel launch (run emission)");
 }
 
@@ -227,7 +248,8 @@ giddy_status_t dzbv_launch(void* stream, const giddy_launch_config_t* cfg, void*
 	cudaStream_t s = as_stream(stream);
 	const uint64_t num_segments = (n + L - 1) / L;
 	workspace_t workspace(s);
-	cudaError_t error = workspace.take((num_segments + 1) * 8 + 64);
+	const uint64_t num_chunks = (num_segments + enc::placement_chunk_tiles - 1) / enc::placement_chunk_tiles;
+	cudaError_t error = workspace.take((num_segments + 1) * 8 + (num_chunks + 1) * 8 + 64);
 	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocFromPoolAsync (variable-width encoder workspace)"); }
 	auto* segment_bytes = static_cast<uint64_t*>(workspace.memory);
 	const unsigned block = cfg->block_dimensions[0] ? cfg->block_dimensions[0] : 256;
@@ -236,7 +258,10 @@ giddy_status_t dzbv_launch(void* stream, const giddy_launch_config_t* cfg, void*
 	enc::variable_width_segment_bytes<U><<<grid, block, 0, s>>>(segment_bytes, x, n, L, min_size, bits, status);
 	giddy_status_t result = launched("kernel launch (variable-width segment sizes)");
 	if (result != GIDDY_SUCCESS) { return result; }
-	enc::exclusive_sum_by_one_block<<<1, 1024, 0, s>>>(segment_bytes, segment_bytes, num_segments);
+	uint64_t* chunk_totals = segment_bytes + num_segments + 1;
+	enc::chunk_exclusive_sums<<<(unsigned) num_chunks, enc::placement_chunk_tiles, 0, s>>>(segment_bytes, chunk_totals, num_segments);
+	enc::run_scan_chunks<false><<<1, 1024, 0, s>>>(chunk_totals, num_chunks, chunk_totals + num_chunks);
+	enc::add_chunk_bases<<<(unsigned) num_chunks, enc::placement_chunk_tiles, 0, s>>>(segment_bytes, chunk_totals, chunk_totals + num_chunks, num_segments);
 	if ((result = launched("kernel launch (segment byte offsets)")) != GIDDY_SUCCESS) { return result; }
 	enc::variable_width_emit<I, U><<<grid, block, 0, s>>>(static_cast<uint8_t*>(data), static_cast<uint_t<I>*>(anchors), static_cast<uint64_t*>(num_bytes_out),
 		x, segment_bytes, n, L, min_size, data_capacity, status);

@@ -135,6 +135,16 @@ __global__ void discard_zero_bytes_fixed_compress(
 // ASCENDING (binary search); a value which is not an entry raises status_unrepresentable.  The dictionary is searched in
 // shared memory when the launch brings enough of it.
 // -------------------------------------------------------------------------------------------------
+constexpr unsigned dictionary_hash_max_entries = 1024;              // dictionaries up to this size are looked up through a hash table
+constexpr unsigned dictionary_hash_slots = 2 * dictionary_hash_max_entries;
+
+template <unsigned U>
+__device__ __forceinline__ unsigned dictionary_hash(uint_t<U> x)
+{
+	uint64_t h = (uint64_t) x * 0x9E3779B97F4A7C15ull; // Fibonacci hashing: the product's high bits
+	return (unsigned)(h >> (64 - 11)) & (dictionary_hash_slots - 1);
+}
+
 template <unsigned IndexSize, unsigned U, unsigned DictionaryIndexSize>
 __global__ void dictionary_compress(
 	uint_t<DictionaryIndexSize>*  __restrict__  compressed,
@@ -144,6 +154,38 @@ __global__ void dictionary_compress(
 	size_type<IndexSize>                        length,
 	unsigned*                                   status)
 {
+	static_assert(dictionary_hash_slots == 2048, "the hash takes 11 bits");
+	bool missing = false;
+	if (num_dictionary_entries != 0 && num_dictionary_entries <= dictionary_hash_max_entries) {
+		// Small dictionaries (the usual case: 256 entries for 1-byte indices): an open-addressing hash table in shared memory,
+		// built by every block -- ~1.3 probes per element where a binary search takes log2(D) dependent steps.
+		__shared__ uint_t<U> slot_keys[dictionary_hash_slots];
+		__shared__ unsigned  slot_indices[dictionary_hash_slots];
+		constexpr unsigned empty = 0xffffffffu;
+		for (unsigned i = threadIdx.x; i < dictionary_hash_slots; i += blockDim.x) { slot_indices[i] = empty; }
+		__syncthreads();
+		// (the dictionary ascends, so equal entries are neighbours: only the first of them is inserted -- the lowest index wins, as
+		// in the search -- and no insertion ever needs to look at another's key)
+		for (unsigned i = threadIdx.x; i < num_dictionary_entries; i += blockDim.x) {
+			const uint_t<U> key = __ldg(dictionary_entries + i);
+			if (i != 0 && __ldg(dictionary_entries + i - 1) == key) { continue; }
+			unsigned h = dictionary_hash<U>(key);
+			while (atomicCAS(&slot_indices[h], empty, i) != empty) { h = (h + 1) & (dictionary_hash_slots - 1); }
+			slot_keys[h] = key;
+		}
+		__syncthreads();
+		encode_elementwise<U, DictionaryIndexSize>(compressed, uncompressed, length, [&](uint64_t, uint_t<U> x) {
+			unsigned h = dictionary_hash<U>(x);
+			while (true) {
+				const unsigned index = slot_indices[h];
+				if (index == empty) { missing = true; return (uint_t<DictionaryIndexSize>) 0; }
+				if (slot_keys[h] == x) { return (uint_t<DictionaryIndexSize>) index; }
+				h = (h + 1) & (dictionary_hash_slots - 1);
+			}
+		});
+		if (missing) { raise(status, status_unrepresentable); }
+		return;
+	}
 	const uint_t<U>* table = dictionary_entries;
 	if ((uint64_t) dynamic_shared_memory_size() >= (uint64_t) num_dictionary_entries * U && num_dictionary_entries != 0) {
 		auto cached = reinterpret_cast<uint_t<U>*>(dynamic_shared_memory);
@@ -151,7 +193,6 @@ __global__ void dictionary_compress(
 		__syncthreads();
 		table = cached;
 	}
-	bool missing = false;
 	encode_elementwise<U, DictionaryIndexSize>(compressed, uncompressed, length, [&](uint64_t, uint_t<U> x) {
 		uint64_t low = 0, high = num_dictionary_entries; // first entry >= x
 		while (low < high) {
@@ -199,14 +240,23 @@ __global__ void frame_of_reference_compress(
 	const int64_t lowest = -((int64_t) 1 << (8 * C - 1)), highest = ((int64_t) 1 << (8 * C - 1)) - 1;
 	const unsigned lane = lane_index();
 	bool overflow = false;
+	constexpr unsigned E = 16 / U; // elements per 16-byte load
 	for (uint64_t s = global_warp_index(); s < num_segments; s += num_warps_in_grid()) {
 		const uint64_t start = s * L;
 		const uint64_t count = minimum<uint64_t>(L, n - start);
 		const int_t<U>* __restrict__ x = uncompressed + start;
+		// whole vectors of the segment go through 16-byte loads (and E * C-byte stores); the rest element by element
+		const bool vectors = is_aligned_to(x, 16) && is_aligned_to(compressed + start, E * C);
+		const uint64_t num_vectors = vectors ? count / E : 0;
 		int64_t c0, c1 = 0;
 		if (Model == model_constant) {
 			int64_t lowest_value = INT64_MAX;
-			for (uint64_t i = lane; i < count; i += warp_size) { const int64_t v = x[i]; lowest_value = v < lowest_value ? v : lowest_value; }
+			for (uint64_t v = lane; v < num_vectors; v += warp_size) {
+				const byte_pack<16> pack = load_pack<16>(x + v * E);
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) { const int64_t value = (int_t<U>) pack.template get<U>(j); lowest_value = value < lowest_value ? value : lowest_value; }
+			}
+			for (uint64_t i = num_vectors * E + lane; i < count; i += warp_size) { const int64_t value = x[i]; lowest_value = value < lowest_value ? value : lowest_value; }
 			c0 = warp_min(lowest_value) - lowest;
 		}
 		else {
@@ -214,9 +264,17 @@ __global__ void frame_of_reference_compress(
 			const int64_t last = (count == L) ? (int64_t) x[L - 1] : (int64_t) uncompressed[n - 1];
 			c1 = (int64_t) rint((double)(last - first) / (double)(L > 1 ? L - 1 : 1));
 			int64_t lowest_residual = INT64_MAX;
-			for (uint64_t i = lane; i < L; i += warp_size) {
-				const int64_t v = (i < count) ? (int64_t) x[i] : (int64_t) uncompressed[n - 1];
-				const int64_t residual = v - (first + c1 * (int64_t) i);
+			for (uint64_t v = lane; v < num_vectors; v += warp_size) {
+				const byte_pack<16> pack = load_pack<16>(x + v * E);
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) {
+					const int64_t residual = (int64_t)(int_t<U>) pack.template get<U>(j) - (first + c1 * (int64_t)(v * E + j));
+					lowest_residual = residual < lowest_residual ? residual : lowest_residual;
+				}
+			}
+			for (uint64_t i = num_vectors * E + lane; i < L; i += warp_size) { // (a short last segment counts as padded with the column's last element)
+				const int64_t value = (i < count) ? (int64_t) x[i] : (int64_t) uncompressed[n - 1];
+				const int64_t residual = value - (first + c1 * (int64_t) i);
 				lowest_residual = residual < lowest_residual ? residual : lowest_residual;
 			}
 			c0 = first + (warp_min(lowest_residual) - lowest);
@@ -225,7 +283,18 @@ __global__ void frame_of_reference_compress(
 			segment_model_coefficients[s * dim] = (int32_t) c0;
 			if (dim == 2) { segment_model_coefficients[s * dim + 1] = (int32_t) c1; }
 		}
-		for (uint64_t i = lane; i < count; i += warp_size) {
+		for (uint64_t v = lane; v < num_vectors; v += warp_size) { // the second pass over the segment: out of L1 / L2
+			const byte_pack<16> pack = load_pack<16>(x + v * E);
+			byte_pack<E * C> out;
+			#pragma unroll
+			for (unsigned j = 0; j < E; j++) {
+				const int64_t offset = (int64_t)(int_t<U>) pack.template get<U>(j) - (c0 + c1 * (int64_t)(v * E + j));
+				if (offset < lowest || offset > highest) { overflow = true; }
+				out.template set<C>(j, (uint_t<C>)(int_t<C>) offset);
+			}
+			store_pack<E * C>(compressed + start + v * E, out);
+		}
+		for (uint64_t i = num_vectors * E + lane; i < count; i += warp_size) {
 			const int64_t offset = (int64_t) x[i] - (c0 + c1 * (int64_t) i);
 			if (offset < lowest || offset > highest) { overflow = true; }
 			compressed[start + i] = (int_t<C>) offset;
@@ -373,77 +442,147 @@ __global__ void __launch_bounds__(run_tile_threads) run_tile_summaries(
 	}
 }
 
-// one block; placement[t] = index of tile t's first run; placement[num_tiles] = the number of runs; open_run_start[t] = start
-// of the run which contains the element before tile t (undefined for tile 0)
-__global__ void run_tile_placement(
-	uint64_t*                  __restrict__  placement,
+// placement[t] = index of tile t's first run; placement[num_tiles] = the number of runs; open_run_start[t] = start of the
+// run which contains the element before tile t (undefined for tile 0).  Two scans over the tile summaries -- the run open at
+// each tile's start is a max-scan of the last-head positions; with it the tile's head count is known, and the placement is
+// the sum-scan of the counts -- each done in three steps over chunks of 1024 tiles (a block per chunk):
+//   run_chunk_last_heads   chunk c: its last natural head                                       (reduce)
+//   run_scan_chunks        one block: exclusive "last non-zero" scan of the chunks' values         (scan of <= a few thousand values)
+//   run_tile_counts        chunk c: open_run_start and head count of every tile; the chunk's total (scan within the chunk + carry)
+//   run_scan_chunks        one block: exclusive sum of the chunks' totals
+//   run_tile_places        chunk c: placement of every tile                                      (scan within the chunk + carry)
+constexpr unsigned placement_chunk_tiles = 1024;
+
+template <typename T, bool LastNonZero>
+__device__ __forceinline__ T block_exclusive_scan_1024(T value, T* shared /* [33] */, T& block_total)
+{
+	// LastNonZero: the nearest preceding non-zero value (0 if none); else the sum of the preceding values
+	const unsigned lane = lane_index(), warp = warp_index_in_block();
+	T inclusive = value;
+	#pragma unroll
+	for (unsigned d = 1; d < warp_size; d <<= 1) {
+		const T y = shuffle_up(inclusive, d);
+		if (lane >= d) { inclusive = LastNonZero ? (inclusive != 0 ? inclusive : y) : (T)(inclusive + y); }
+	}
+	if (lane == warp_size - 1) { shared[warp] = inclusive; }
+	__syncthreads();
+	if (warp == 0) {
+		T w = (lane < warps_per_block()) ? shared[lane] : (T) 0;
+		T scanned = w;
+		#pragma unroll
+		for (unsigned d = 1; d < warp_size; d <<= 1) {
+			const T y = shuffle_up(scanned, d);
+			if (lane >= d) { scanned = LastNonZero ? (scanned != 0 ? scanned : y) : (T)(scanned + y); }
+		}
+		// exclusive over warps
+		T before = shuffle_up(scanned, 1);
+		if (lane == 0) { before = 0; }
+		shared[lane] = before;
+		if (lane == warp_size - 1) { shared[warp_size] = scanned; }
+	}
+	__syncthreads();
+	T before_lane = shuffle_up(inclusive, 1);
+	if (lane == 0) { before_lane = 0; }
+	const T carried = shared[warp];
+	const T result = LastNonZero ? (before_lane != 0 ? before_lane : carried) : (T)(carried + before_lane);
+	block_total = shared[warp_size];
+	__syncthreads();
+	return result;
+}
+
+__global__ void __launch_bounds__(placement_chunk_tiles) run_chunk_last_heads(
+	uint64_t* __restrict__ chunk_last, const run_tile_summary_t* __restrict__ summaries, uint64_t num_tiles)
+{
+	__shared__ uint64_t shared[warp_size + 1];
+	const uint64_t tile = (uint64_t) blockIdx.x * placement_chunk_tiles + threadIdx.x;
+	const uint64_t last = (tile < num_tiles) ? summaries[tile].last_head : no_position;
+	uint64_t total;
+	block_exclusive_scan_1024<uint64_t, true>(last == no_position ? 0 : last + 1, shared, total);
+	if (threadIdx.x == 0) { chunk_last[blockIdx.x] = total; } // position + 1 of the chunk's last natural head, 0 if it has none
+}
+
+template <bool LastNonZero>
+__global__ void __launch_bounds__(1024) run_scan_chunks(uint64_t* __restrict__ values, uint64_t count, uint64_t* __restrict__ total_out)
+{
+	// in place: values[c] <- exclusive scan; sequential over batches of 1024 chunks with a running carry
+	__shared__ uint64_t shared[warp_size + 1];
+	uint64_t carry = 0;
+	for (uint64_t base = 0; base < count; base += 1024) {
+		const uint64_t c = base + threadIdx.x;
+		const uint64_t mine = (c < count) ? values[c] : 0;
+		uint64_t total;
+		const uint64_t before = block_exclusive_scan_1024<uint64_t, LastNonZero>(mine, shared, total);
+		if (c < count) { values[c] = LastNonZero ? (before != 0 ? before : carry) : carry + before; }
+		carry = LastNonZero ? (total != 0 ? total : carry) : carry + total;
+	}
+	if (threadIdx.x == 0 && total_out != nullptr) { *total_out = carry; }
+}
+
+__global__ void __launch_bounds__(placement_chunk_tiles) run_tile_counts(
+	uint64_t*                  __restrict__  counts,          // per tile: its number of heads
 	uint64_t*                  __restrict__  open_run_start,
+	uint64_t*                  __restrict__  chunk_totals,
+	const uint64_t*            __restrict__  chunk_open,      // exclusive last-non-zero scan of chunk_last
 	const run_tile_summary_t*  __restrict__  summaries,
 	uint64_t                                 num_tiles,
 	uint64_t                                 length,
 	uint64_t                                 max_run_length)
 {
-	__shared__ uint64_t totals[warp_size + 1];
-	__shared__ uint64_t carry_last[warp_size + 1];
-	const uint64_t per_thread = (num_tiles + blockDim.x - 1) / blockDim.x;
-	const uint64_t first = minimum<uint64_t>((uint64_t) threadIdx.x * per_thread, num_tiles);
-	const uint64_t past_last = minimum<uint64_t>(first + per_thread, num_tiles);
-	// exclusive max-scan of (last natural head + 1): the natural run open at each tile's start
-	uint64_t my_last = 0;
-	for (uint64_t t = first; t < past_last; t++) { const uint64_t l = summaries[t].last_head; if (l != no_position) { my_last = l + 1; } }
-	// scan of "last non-zero" across threads: carry = the nearest preceding thread's non-zero value
-	{
-		const unsigned lane = lane_index(), warp = warp_index_in_block();
-		uint64_t v = my_last;
-		#pragma unroll
-		for (unsigned d = 1; d < warp_size; d <<= 1) {
-			const uint64_t y = __shfl_up_sync(full_mask, (unsigned long long) v, d);
-			if (lane >= d && v == 0) { v = y; }
-		}
-		if (lane == warp_size - 1) { carry_last[warp] = v; }
-		__syncthreads();
-		if (warp == 0) {
-			uint64_t w = (lane < warps_per_block()) ? carry_last[lane] : 0;
-			#pragma unroll
-			for (unsigned d = 1; d < warp_size; d <<= 1) {
-				const uint64_t y = __shfl_up_sync(full_mask, (unsigned long long) w, d);
-				if (lane >= d && w == 0) { w = y; }
-			}
-			carry_last[lane] = w;
-		}
-		__syncthreads();
-		uint64_t before = __shfl_up_sync(full_mask, (unsigned long long) v, 1); // inclusive value of the previous lane
-		if (lane == 0) { before = (warp == 0) ? 0 : carry_last[warp - 1]; }
-		else if (before == 0 && warp != 0) { before = carry_last[warp - 1]; }
-		my_last = before; // the value carried INTO this thread's first tile
-		__syncthreads();
-	}
-	// per tile: its head count given the open run; thread-local sums
-	uint64_t sum = 0, open = my_last;
-	for (uint64_t t = first; t < past_last; t++) {
-		const run_tile_summary_t s = summaries[t];
-		const uint64_t tile_start = t * run_tile_elements;
+	__shared__ uint64_t shared[warp_size + 1];
+	const uint64_t tile = (uint64_t) blockIdx.x * placement_chunk_tiles + threadIdx.x;
+	const bool valid = tile < num_tiles;
+	run_tile_summary_t s = { no_position, no_position, 0 };
+	if (valid) { s = summaries[tile]; }
+	uint64_t unused;
+	uint64_t open = block_exclusive_scan_1024<uint64_t, true>(s.last_head == no_position ? 0 : s.last_head + 1, shared, unused);
+	if (open == 0) { open = chunk_open[blockIdx.x]; }
+	const uint64_t origin = (open == 0) ? 0 : open - 1;
+	uint64_t count = 0;
+	if (valid) {
+		const uint64_t tile_start = tile * run_tile_elements;
 		const uint64_t tile_end = minimum<uint64_t>(tile_start + run_tile_elements, length);
 		const uint64_t prefix_end = (s.first_head == no_position) ? tile_end : s.first_head;
-		const uint64_t origin = (open == 0) ? 0 : open - 1; // (tile 0 begins with a head at position 0: no prefix there)
-		sum += s.heads_from_first + ((t == 0) ? 0 : split_points_between(origin, tile_start, prefix_end, max_run_length));
-		if (s.last_head != no_position) { open = s.last_head + 1; }
+		count = s.heads_from_first + ((tile == 0) ? 0 : split_points_between(origin, tile_start, prefix_end, max_run_length));
+		counts[tile] = count;
+		open_run_start[tile] = origin;
 	}
 	uint64_t total;
-	uint64_t running = block_exclusive_sum(sum, totals, total);
-	open = my_last;
-	for (uint64_t t = first; t < past_last; t++) {
-		const run_tile_summary_t s = summaries[t];
-		const uint64_t tile_start = t * run_tile_elements;
-		const uint64_t tile_end = minimum<uint64_t>(tile_start + run_tile_elements, length);
-		const uint64_t prefix_end = (s.first_head == no_position) ? tile_end : s.first_head;
-		const uint64_t origin = (open == 0) ? 0 : open - 1;
-		placement[t] = running;
-		open_run_start[t] = origin;
-		running += s.heads_from_first + ((t == 0) ? 0 : split_points_between(origin, tile_start, prefix_end, max_run_length));
-		if (s.last_head != no_position) { open = s.last_head + 1; }
-	}
-	if (threadIdx.x == 0) { placement[num_tiles] = total; }
+	block_exclusive_scan_1024<uint64_t, false>(count, shared, total);
+	if (threadIdx.x == 0) { chunk_totals[blockIdx.x] = total; }
+}
+
+__global__ void __launch_bounds__(placement_chunk_tiles) run_tile_places(
+	uint64_t* __restrict__ placement /* in: counts, out: exclusive sums; [num_tiles] = total */, const uint64_t* __restrict__ chunk_bases,
+	const uint64_t* __restrict__ grand_total, uint64_t num_tiles)
+{
+	__shared__ uint64_t shared[warp_size + 1];
+	const uint64_t tile = (uint64_t) blockIdx.x * placement_chunk_tiles + threadIdx.x;
+	const uint64_t count = (tile < num_tiles) ? placement[tile] : 0;
+	uint64_t unused;
+	const uint64_t before = block_exclusive_scan_1024<uint64_t, false>(count, shared, unused);
+	if (tile < num_tiles) { placement[tile] = chunk_bases[blockIdx.x] + before; }
+	if (blockIdx.x == 0 && threadIdx.x == 0) { placement[num_tiles] = *grand_total; }
+}
+
+// Exclusive prefix sums of an array of counts, in place, in three steps over chunks of 1024 (values[count] = the total):
+// chunk_exclusive_sums -> run_scan_chunks<false> on the chunk totals -> add_chunk_bases.
+__global__ void __launch_bounds__(placement_chunk_tiles) chunk_exclusive_sums(uint64_t* __restrict__ values, uint64_t* __restrict__ chunk_totals, uint64_t count)
+{
+	__shared__ uint64_t shared[warp_size + 1];
+	const uint64_t i = (uint64_t) blockIdx.x * placement_chunk_tiles + threadIdx.x;
+	const uint64_t mine = (i < count) ? values[i] : 0;
+	uint64_t total;
+	const uint64_t before = block_exclusive_scan_1024<uint64_t, false>(mine, shared, total);
+	if (i < count) { values[i] = before; }
+	if (threadIdx.x == 0) { chunk_totals[blockIdx.x] = total; }
+}
+
+__global__ void __launch_bounds__(placement_chunk_tiles) add_chunk_bases(uint64_t* __restrict__ values, const uint64_t* __restrict__ chunk_bases,
+	const uint64_t* __restrict__ grand_total, uint64_t count)
+{
+	const uint64_t i = (uint64_t) blockIdx.x * placement_chunk_tiles + threadIdx.x;
+	if (i < count) { values[i] += chunk_bases[blockIdx.x]; }
+	if (blockIdx.x == 0 && threadIdx.x == 0) { values[count] = *grand_total; }
 }
 
 // pass 2: every head writes its run's value and start.  A thread owns run_tile_per_thread CONSECUTIVE elements here, so
@@ -496,6 +635,149 @@ __global__ void __launch_bounds__(run_tile_threads) run_emit(
 				index++;
 			}
 		}
+	}
+}
+
+// ---- the fast path of the run encoders: run lengths limited to at least a tile's length (or not at all) ------------------
+// Then a run which begins in a tile has no split point inside that tile, and the run which is open at a tile's start has at most
+// one: heads are the natural ones plus, per tile, at most one computed position.  A thread takes 16 CONSECUTIVE elements with
+// 16-byte loads, turns them into a 16-bit mask of heads (the element before its first comes from the previous lane by shuffle),
+// and everything else is bit arithmetic on masks.  run_emit_fast compacts the tile's (value, position) pairs through shared
+// memory so that they leave as contiguous, coalesced stores.
+
+template <unsigned U>
+__device__ __forceinline__ void load_16_elements(uint_t<U> (&v)[run_tile_per_thread], const uint_t<U>* __restrict__ x, uint64_t first, uint64_t limit, bool vector_loads)
+{
+	static_assert(run_tile_per_thread == 16, "a thread's elements are loaded as 16 x U bytes");
+	if (vector_loads && first + run_tile_per_thread <= limit) {
+		const byte_pack<16 * U> pack = load_pack<16 * U>(x + first);
+		#pragma unroll
+		for (unsigned j = 0; j < run_tile_per_thread; j++) { v[j] = pack.template get<U>(j); }
+	}
+	else {
+		#pragma unroll
+		for (unsigned j = 0; j < run_tile_per_thread; j++) { v[j] = (first + j < limit) ? x[first + j] : (uint_t<U>) 0; }
+	}
+}
+
+// bit j set: element first + j begins a natural run (elements at or beyond `limit` never do)
+template <unsigned U>
+__device__ __forceinline__ unsigned natural_heads_of_16(const uint_t<U> (&v)[run_tile_per_thread], const uint_t<U>* __restrict__ x, uint64_t first, uint64_t limit)
+{
+	// the element before this thread's first: the previous lane's last, except for a warp's first lane
+	uint_t<U> before = shuffle_up(v[run_tile_per_thread - 1], 1);
+	if (lane_index() == 0 && first != 0 && first < limit) { before = x[first - 1]; }
+	unsigned mask = 0;
+	#pragma unroll
+	for (unsigned j = 0; j < run_tile_per_thread; j++) {
+		const bool head = (j == 0) ? (first == 0 || v[0] != before) : (v[j] != v[j - 1]);
+		if (head && first + j < limit) { mask |= 1u << j; }
+	}
+	return mask;
+}
+
+template <unsigned U>
+__global__ void __launch_bounds__(run_tile_threads) run_tile_summaries_fast(
+	run_tile_summary_t*  __restrict__  summaries,
+	const uint_t<U>*     __restrict__  x,
+	uint64_t                           length)
+{
+	__shared__ uint64_t shared_first[run_tile_threads / warp_size], shared_last[run_tile_threads / warp_size];
+	__shared__ unsigned shared_count[run_tile_threads / warp_size];
+	const bool vector_loads = is_aligned_to(x, 16);
+	const uint64_t num_tiles = (length + run_tile_elements - 1) / run_tile_elements;
+	for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+		const uint64_t tile_start = tile * run_tile_elements;
+		const uint64_t first = tile_start + (uint64_t) threadIdx.x * run_tile_per_thread;
+		uint_t<U> v[run_tile_per_thread];
+		load_16_elements<U>(v, x, first, length, vector_loads);
+		const unsigned mask = natural_heads_of_16<U>(v, x, first, length);
+		// warp: first head (min), last head + 1 (max), head count (sum)
+		uint64_t lowest = mask ? first + (__ffs(mask) - 1) : no_position;
+		uint64_t highest = mask ? first + (32 - __clz(mask)) : 0; // position + 1
+		unsigned count = __popc(mask);
+		#pragma unroll
+		for (unsigned d = 16; d > 0; d >>= 1) {
+			const uint64_t l = __shfl_xor_sync(full_mask, (unsigned long long) lowest, d);
+			const uint64_t h = __shfl_xor_sync(full_mask, (unsigned long long) highest, d);
+			lowest = l < lowest ? l : lowest; highest = h > highest ? h : highest;
+			count += __shfl_xor_sync(full_mask, count, d);
+		}
+		if (lane_index() == 0) { shared_first[warp_index_in_block()] = lowest; shared_last[warp_index_in_block()] = highest; shared_count[warp_index_in_block()] = count; }
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			for (unsigned w = 1; w < run_tile_threads / warp_size; w++) {
+				lowest = shared_first[w] < lowest ? shared_first[w] : lowest;
+				highest = shared_last[w] > highest ? shared_last[w] : highest;
+				count += shared_count[w];
+			}
+			summaries[tile] = { lowest, highest == 0 ? no_position : highest - 1, count };
+		}
+		__syncthreads();
+	}
+}
+
+template <unsigned U, typename Start>
+__global__ void __launch_bounds__(run_tile_threads) run_emit_fast(
+	uint_t<U>*        __restrict__  run_data,
+	Start*            __restrict__  starts,
+	const uint_t<U>*  __restrict__  x,
+	const uint64_t*   __restrict__  placement,
+	const uint64_t*   __restrict__  open_run_start,
+	const run_tile_summary_t*  __restrict__  summaries,
+	uint64_t                        length,
+	uint64_t                        max_run_length,   // 0, or at least run_tile_elements
+	uint64_t                        run_capacity,
+	unsigned*                       status)
+{
+	__shared__ unsigned   warp_totals[run_tile_threads / warp_size + 1];
+	__shared__ uint_t<U>  staged_values[run_tile_elements];
+	__shared__ uint16_t   staged_positions[run_tile_elements];
+	const bool vector_loads = is_aligned_to(x, 16);
+	const uint64_t num_tiles = (length + run_tile_elements - 1) / run_tile_elements;
+	for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+		const uint64_t tile_start = tile * run_tile_elements;
+		const uint64_t first = tile_start + (uint64_t) threadIdx.x * run_tile_per_thread;
+		uint_t<U> v[run_tile_per_thread];
+		load_16_elements<U>(v, x, first, length, vector_loads);
+		unsigned mask = natural_heads_of_16<U>(v, x, first, length);
+		// the one split point this tile can hold: in the part of the open run which precedes the tile's first natural head
+		if (max_run_length != 0 && tile != 0) {
+			const uint64_t origin = open_run_start[tile];
+			const uint64_t steps = (tile_start - origin + max_run_length - 1) / max_run_length; // smallest k with origin + k * M >= tile_start
+			const uint64_t split = origin + (steps == 0 ? max_run_length : steps * max_run_length);
+			const uint64_t first_head = summaries[tile].first_head;
+			const uint64_t prefix_end = (first_head == no_position) ? minimum<uint64_t>(tile_start + run_tile_elements, length) : first_head;
+			if (split < prefix_end && split >= first && split < first + run_tile_per_thread) { mask |= 1u << (unsigned)(split - first); }
+		}
+		// exclusive scan of the head counts over the block
+		const unsigned count = __popc(mask);
+		const unsigned inclusive = warp_inclusive_sum(count);
+		if (lane_index() == warp_size - 1) { warp_totals[warp_index_in_block()] = inclusive; }
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			unsigned running = 0;
+			for (unsigned w = 0; w < run_tile_threads / warp_size; w++) { const unsigned t = warp_totals[w]; warp_totals[w] = running; running += t; }
+			warp_totals[run_tile_threads / warp_size] = running;
+		}
+		__syncthreads();
+		unsigned slot = warp_totals[warp_index_in_block()] + inclusive - count;
+		const unsigned tile_heads = warp_totals[run_tile_threads / warp_size];
+		#pragma unroll
+		for (unsigned j = 0; j < run_tile_per_thread; j++) { // (statically indexed: the elements stay in registers)
+			if ((mask >> j) & 1u) {
+				staged_values[slot] = v[j];
+				staged_positions[slot] = (uint16_t)(threadIdx.x * run_tile_per_thread + j);
+				slot++;
+			}
+		}
+		__syncthreads();
+		const uint64_t base = placement[tile];
+		for (unsigned e = threadIdx.x; e < tile_heads; e += run_tile_threads) {
+			if (base + e < run_capacity) { run_data[base + e] = staged_values[e]; starts[base + e] = (Start)(tile_start + staged_positions[e]); }
+			else { raise(status, status_capacity); }
+		}
+		__syncthreads();
 	}
 }
 
@@ -668,13 +950,26 @@ __global__ void variable_width_pack_sizes(
 	const uint64_t per_container = (8 * CS) / bits;
 	const uint64_t num_containers = (length + per_container - 1) / per_container;
 	const uint64_t field_mask = (bits >= 64) ? ~0ull : ((1ull << bits) - 1);
+	const bool sixteen = per_container == run_tile_per_thread && is_aligned_to(x, 16); // 2-bit fields in 32-bit containers, 4-bit in 64-bit: one 16-element load
 	for (uint64_t c = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; c < num_containers; c += (uint64_t) gridDim.x * blockDim.x) {
 		uint64_t container = 0;
-		for (uint64_t k = 0; k < per_container; k++) {
-			const uint64_t i = c * per_container + k;
-			if (i >= length) { break; }
-			const unsigned size = max(significant_bytes<U>(x[i]), min_size);
-			container |= ((uint64_t)(size - min_size) & field_mask) << (k * bits);
+		if (sixteen) {
+			uint_t<U> v[run_tile_per_thread];
+			load_16_elements<U>(v, x, c * run_tile_per_thread, length, true);
+			#pragma unroll
+			for (unsigned k = 0; k < run_tile_per_thread; k++) {
+				if (c * run_tile_per_thread + k < length) {
+					container |= ((uint64_t)(max(significant_bytes<U>(v[k]), min_size) - min_size) & field_mask) << (k * bits);
+				}
+			}
+		}
+		else {
+			for (uint64_t k = 0; k < per_container; k++) {
+				const uint64_t i = c * per_container + k;
+				if (i >= length) { break; }
+				const unsigned size = max(significant_bytes<U>(x[i]), min_size);
+				container |= ((uint64_t)(size - min_size) & field_mask) << (k * bits);
+			}
 		}
 		packed_element_sizes[c] = (uint_t<CS>) container;
 	}

@@ -52,6 +52,10 @@ probe)
 	timeout 900 python benchmarks/patched_probe.py --out $OUT/${TAG}_patched_probe.json 2>&1 | tee $OUT/${TAG}_patched_probe.txt ;;
 configs)
 	timeout 1500 python benchmarks/configs.py --out $OUT/${TAG}_configs.json 2>&1 | tee $OUT/${TAG}_configs.txt ;;
+launches_compress)
+	timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches_compress.csv \
+		python benchmarks/compress_sweep.py --repeats 1 --out $OUT/${TAG}_compress_ncu.json > $OUT/${TAG}_launches_compress.log 2>&1
+	python scripts/launch_list_summary.py $OUT/${TAG}_launches_compress.csv $OUT/${TAG}_launches_compress.md; cut -c1-200 $OUT/${TAG}_launches_compress.md ;;
 compress)
 	timeout 900 python benchmarks/compress_sweep.py --out $OUT/${TAG}_compress_sweep.json 2>&1 | tee $OUT/${TAG}_compress_sweep.txt ;;
 sweep)
