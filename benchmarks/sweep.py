@@ -100,12 +100,13 @@ def main():
     p.add_argument("--only", default="")
     p.add_argument("--no-reference", action="store_true")
     p.add_argument("--single-launch", action="store_true", help="one untimed launch per workload (for ncu captures)")
+    p.add_argument("--library", default="", help="path of another build of the product library (make variant ...)")
     args = p.parse_args()
 
     import torch
     import cases
     import libgiddy_b200 as g
-    product = g.default_library()
+    product = g.Library(args.library) if args.library else g.default_library()
     reference_path = os.path.join(ROOT, "oracle", "_ref", "libgiddy_ref.so")
     reference = g.Library(reference_path) if os.path.exists(reference_path) and not args.no_reference else None
     try:

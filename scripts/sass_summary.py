@@ -4,7 +4,7 @@
   profiles/sass_<tag>_summary.md   one row per kernel instantiation: registers, and how many of the instructions which
                                    carry the design are in it (128/256-bit global accesses, TMA bulk copies, mbarrier
                                    waits, shuffles, votes, shared-memory atomics, barriers)
-  profiles/sass_<tag>/<kernel>.sass the full listing of the instantiations the BASELINE configurations use
+  profiles/sass_<tag>/<kernel>.sass.gz the full listing of the instantiations the BASELINE configurations use
 
     make sass && python scripts/sass_summary.py r01
 """
@@ -28,6 +28,9 @@ HEADLINE = [
     "discard_zero_bytes_variable_decompress<4, 4, 4>", "delta_of_discard_zero_bytes_variable_decompress<4, 8, 4, 4>",
     "incidence_bitmaps_decompress<4, 4, 2, true>", "scatter<4, 8, 4>", "compressed_indices_scatter<4, 4, 4, 4>",
     "patched_dictionary_decompress<4, 8, 1>", "patched_frame_of_reference_decompress<4, 4, 2, 1, 4>", "expand_compressed_indices<4, 4, 4>", "patched_detail::patch_tile_ranges<4>",
+    "patched_detail::expand_and_index_compressed_indices<4, 4, 4>",
+    "encoders::run_tile_summaries_fast<4>", "encoders::run_emit_fast<4, unsigned long>", "encoders::delta_compress<4, 8, 4>",
+    "encoders::frame_of_reference_compress<4, 4, 2, 0>", "encoders::dictionary_compress<4, 8, 1>", "encoders::variable_width_emit<4, 4>",
 ]
 
 
@@ -57,7 +60,8 @@ def main():
             rows.append((name, registers.get(mangled, ("?", "?")), instructions, counts))
             if any(name.replace("u>", ">").replace("u,", ",") == h for h in HEADLINE):
                 safe = re.sub(r"[^A-Za-z0-9]+", "_", name).strip("_")
-                with open(os.path.join(out_dir, safe + ".sass"), "w") as f:
+                import gzip
+                with gzip.open(os.path.join(out_dir, safe + ".sass.gz"), "wt") as f:  # (gzip'ed: listings are evidence, not reading matter)
                     f.write("Function : %s\n(%s; nvcc 12.9 -O3 -gencode arch=compute_100a,code=sm_100a)\n%s" % (name, mangled, body))
     rows.sort()
     with open(os.path.join(ROOT, "profiles", "sass_%s_summary.md" % tag), "w") as f:
