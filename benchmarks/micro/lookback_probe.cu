@@ -35,9 +35,12 @@ void run(size_t n, int blocks_per_sm, bool static_tiles, const char* label)
 		CHECK(cudaMemsetAsync(workspace, 0, workspace_bytes));
 		if (static_tiles) {
 			void* arguments[] = { &out, &in, &anchor, &n32, &n32, &workspace };
-			CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernels::delta_decompress_long_segments<4, U, C, true>), dim3(grid), dim3(threads), arguments, 0, 0));
+			const size_t staging = GIDDY_DELTA_LOOK_BACK_SHARED_BYTES(U, C, threads);
+			const void* kernel = reinterpret_cast<const void*>(kernels::delta_decompress_long_segments_staged<4, U, C>);
+			CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staging));
+			CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(threads), arguments, staging, 0));
 		}
-		else { kernels::delta_decompress_long_segments<4, U, C, false><<<grid, threads>>>(out, in, anchor, n32, n32, workspace); }
+		else { kernels::delta_decompress_long_segments<4, U, C><<<grid, threads>>>(out, in, anchor, n32, n32, workspace); }
 	};
 	launch();
 	CHECK(cudaDeviceSynchronize());

@@ -54,6 +54,11 @@
 #ifndef GIDDY_DELTA_LOOK_BACK_WINDOW
 #define GIDDY_DELTA_LOOK_BACK_WINDOW 4             /* descriptors inspected per lane per look-back round */
 #endif
+#ifndef GIDDY_DELTA_LOOK_BACK_STAGES
+#define GIDDY_DELTA_LOOK_BACK_STAGES 2             /* tiles of deltas a CTA of the cooperative kernel stages in shared memory */
+#endif
+/* dynamic shared memory of the staged kernel: the deltas of a tile are tile elements x C bytes */
+#define GIDDY_DELTA_LOOK_BACK_SHARED_BYTES(U, C, threads) (GIDDY_DELTA_LOOK_BACK_STAGES * GIDDY_DELTA_TILE_ELEMENTS(U, threads) * (C))
 #define GIDDY_DELTA_TILE_ELEMENTS(U, threads) ((threads) * GIDDY_DELTA_LOOK_BACK_ROWS * (16 / (U)))
 #define GIDDY_DELTA_USES_LOOK_BACK(length, segment_length, U) \
 	((segment_length) >= 2 * GIDDY_DELTA_TILE_ELEMENTS(U, GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS) && \

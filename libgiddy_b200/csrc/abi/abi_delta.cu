@@ -10,7 +10,7 @@ using namespace giddy::abi;
 namespace {
 
 using delta_launcher_t = giddy_status_t (*)(void*, const giddy_launch_config_t*, void*, const void*, const void*, uint64_t, uint64_t);
-using delta_long_launcher_t = giddy_status_t (*)(void*, const giddy_launch_config_t*, void*, const void*, const void*, uint64_t, uint64_t, void*);
+using delta_long_launcher_t = giddy_status_t (*)(void*, const giddy_launch_config_t*, void*, const void*, const void*, uint64_t, uint64_t, void*, size_t);
 struct delta_entry_t { unsigned I, U, C; const void* kernel; delta_launcher_t launch; delta_long_launcher_t launch_long; };
 
 template <unsigned I, unsigned U, unsigned C>
@@ -22,49 +22,65 @@ giddy_status_t delta_launch(void* stream, const giddy_launch_config_t* cfg, void
 }
 // How many CTAs of `block` threads of `kernel` fit the current device at once, if grids can be launched cooperatively there
 // (0 if not).  Asked of the runtime once per (device, kernel, block size) and thread.
-unsigned resident_blocks(const void* kernel, unsigned block)
+unsigned resident_blocks(const void* kernel, unsigned block, unsigned dynamic_shared_memory)
 {
-	struct key_t { int device; const void* kernel; unsigned block; };
+	struct key_t { int device; const void* kernel; unsigned block, shared; };
 	struct entry_t { key_t key; unsigned resident; };
 	static thread_local ::std::vector<entry_t> known;
 	int device = 0;
 	if (cudaGetDevice(&device) != cudaSuccess) { return 0; }
-	for (const auto& e : known) { if (e.key.device == device && e.key.kernel == kernel && e.key.block == block) { return e.resident; } }
+	for (const auto& e : known) { if (e.key.device == device && e.key.kernel == kernel && e.key.block == block && e.key.shared == dynamic_shared_memory) { return e.resident; } }
 	int supported = 0, multiprocessors = 0, per_multiprocessor = 0;
 	unsigned resident = 0;
 	if (cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, device) == cudaSuccess && supported != 0 &&
 		cudaDeviceGetAttribute(&multiprocessors, cudaDevAttrMultiProcessorCount, device) == cudaSuccess &&
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_multiprocessor, kernel, (int) block, 0) == cudaSuccess) {
+		ensure_dynamic_shared_memory(kernel, dynamic_shared_memory) == cudaSuccess &&
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_multiprocessor, kernel, (int) block, dynamic_shared_memory) == cudaSuccess) {
 		resident = (unsigned) multiprocessors * (unsigned) per_multiprocessor;
 	}
 	else { cudaGetLastError(); }
-	known.push_back({ { device, kernel, block }, resident });
+	known.push_back({ { device, kernel, block, dynamic_shared_memory }, resident });
 	return resident;
 }
 
 template <unsigned I, unsigned U, unsigned C>
 giddy_status_t delta_long_launch(void* stream, const giddy_launch_config_t* cfg, void* out, const void* in, const void* anchors, uint64_t n, uint64_t L,
-	void* workspace)
+	void* workspace, size_t workspace_bytes)
 {
 	auto out_ = static_cast<uint_t<U>*>(out);
 	auto in_ = static_cast<const uint_t<C>*>(in);
 	auto anchors_ = static_cast<const uint_t<U>*>(anchors);
 	size_type<I> n_ = (size_type<I>) n, L_ = (size_type<I>) L;
-	// statically assigned tiles: every CTA must be resident, which a cooperative launch of at most
-	// (CTAs per multiprocessor) x (multiprocessors) CTAs guarantees
-	const void* kernel = reinterpret_cast<const void*>(&kernels::delta_decompress_long_segments<I, U, C, true>);
-	const unsigned block = cfg->block_dimensions[0];
-	const unsigned resident = resident_blocks(kernel, block);
-	if (resident > 0) {
-		const unsigned grid = cfg->grid_dimensions[0] < resident ? cfg->grid_dimensions[0] : resident;
-		void* arguments[] = { &out_, &in_, &anchors_, &n_, &L_, &workspace };
-		const cudaError_t error = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(block), arguments, 0, static_cast<cudaStream_t>(stream));
-		if (error == cudaSuccess) { return GIDDY_SUCCESS; }
-		// (MPS / green-context SM limits can refuse a cooperative grid which the occupancy query allowed: fall back to the
-		// ticket-counter kernel, which is correct under any residency)
-		cudaGetLastError();
+	cudaError_t error = cudaMemsetAsync(workspace, 0, workspace_bytes, static_cast<cudaStream_t>(stream));
+	if (error != cudaSuccess) { return fail_cuda(error, "cudaMemsetAsync (Delta look-back workspace)"); }
+	// Columns aligned for bulk copies: statically assigned tiles, the deltas staged in shared memory.  Every CTA must be
+	// resident, which a cooperative launch of at most (CTAs per multiprocessor) x (multiprocessors) CTAs guarantees.
+	if (kernels::look_back_shapes<U, C>::wide_pieces(out, in, L)) {
+		const void* kernel = reinterpret_cast<const void*>(&kernels::delta_decompress_long_segments_staged<I, U, C>);
+		const unsigned block = cfg->block_dimensions[0];
+		const unsigned staging = (unsigned) GIDDY_DELTA_LOOK_BACK_SHARED_BYTES(U, C, block);
+		const unsigned resident = resident_blocks(kernel, block, staging);
+		if (resident > 0) {
+			unsigned grid = cfg->grid_dimensions[0] < resident ? cfg->grid_dimensions[0] : resident;
+			// whole waves: CTA b takes tiles b, b + grid, ..., so with T tiles in ceil(T / grid) waves, ceil(T / waves) CTAs
+			// finish together where `grid` CTAs would leave most of the last wave idle
+			const uint64_t tile_elements = GIDDY_DELTA_TILE_ELEMENTS(U, block);
+			const uint64_t num_segments = (n + L - 1) / L;
+			const uint64_t num_tiles = (num_segments - 1) * ((L + tile_elements - 1) / tile_elements) +
+				((n - (num_segments - 1) * L) + tile_elements - 1) / tile_elements;
+			if (num_tiles > grid) {
+				const uint64_t waves = (num_tiles + grid - 1) / grid;
+				grid = (unsigned) ((num_tiles + waves - 1) / waves);
+			}
+			void* arguments[] = { &out_, &in_, &anchors_, &n_, &L_, &workspace };
+			error = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(block), arguments, staging, static_cast<cudaStream_t>(stream));
+			if (error == cudaSuccess) { return GIDDY_SUCCESS; }
+			// (MPS / green-context SM limits can refuse a cooperative grid which the occupancy query allowed: fall back to the
+			// ticket-counter kernel, which is correct under any residency)
+			cudaGetLastError();
+		}
 	}
-	return launch(kernels::delta_decompress_long_segments<I, U, C, false>, stream, cfg, out_, in_, anchors_, n_, L_, workspace);
+	return launch(kernels::delta_decompress_long_segments<I, U, C>, stream, cfg, out_, in_, anchors_, n_, L_, workspace);
 }
 #define DELTA_ENTRY(I, U, C) { I, U, C, reinterpret_cast<const void*>(&kernels::delta_decompress<I, U, C>), &delta_launch<I, U, C>, &delta_long_launch<I, U, C> }
 #define DELTA_ENTRIES(I) DELTA_ENTRY(I, 2, 1), DELTA_ENTRY(I, 4, 1), DELTA_ENTRY(I, 4, 2), DELTA_ENTRY(I, 8, 1), DELTA_ENTRY(I, 8, 2), DELTA_ENTRY(I, 8, 4)
@@ -117,9 +133,7 @@ extern "C" giddy_status_t giddy_b200_delta_launch(
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	cudaError_t error = allocate_workspace(&workspace, workspace_bytes, s);
 	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocFromPoolAsync (Delta look-back workspace)"); }
-	error = cudaMemsetAsync(workspace, 0, workspace_bytes, s);
-	if (error != cudaSuccess) { cudaFreeAsync(workspace, s); return fail_cuda(error, "cudaMemsetAsync (Delta look-back workspace)"); }
-	status = e->launch_long(stream, &long_config, decompressed, compressed_input, anchor_values, length, segment_length, workspace);
+	status = e->launch_long(stream, &long_config, decompressed, compressed_input, anchor_values, length, segment_length, workspace, workspace_bytes);
 	error = cudaFreeAsync(workspace, s);
 	if (status == GIDDY_SUCCESS && error != cudaSuccess) { return fail_cuda(error, "cudaFreeAsync (Delta look-back workspace)"); }
 	return status;

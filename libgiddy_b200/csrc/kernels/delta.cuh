@@ -124,12 +124,15 @@ __global__ void delta_decompress(
 //     in one 16-byte access; a torn pair shows two different statuses and is polled again);
 //   * a warp inspects look_back_window x 32 predecessors per round trip, so that the distance to the
 //     inclusive-prefix wavefront (tiles started per L2 round trip, ~100 at HBM speed) is covered in one round;
-//   * tiles are large (look_back_rows 16-byte vectors per thread), and the next tile's deltas are already on
-//     their way from HBM while this tile looks back.
+//   * tiles are large (look_back_rows 16-byte vectors per thread);
+//   * (cooperative launches) the deltas of the next `look_back_stages` tiles are staged in shared memory by TMA
+//     bulk copies, and a tile's aggregate is published a whole scan-and-store phase before its own look-back
+//     begins -- by then the neighbouring CTAs' aggregates are normally there.
 //
 // Persistent CTAs; a tile's predecessors are always running or done, so the spin-waits cannot deadlock: either
 // the grid is launched cooperatively (all CTAs resident) and CTA b takes tiles b, b + grid, ..., or tiles are
-// handed out in order through a ticket counter (any grid size).
+// handed out in order through a ticket counter (any grid size; drawing tickets ahead of time is not an option: a
+// drawn but unstarted tile stalls all its successors, and the stalls chain up -- measured 20x slower).
 //
 // workspace: 32 zeroed bytes (the ticket counter) followed by one zeroed 16-byte descriptor per tile;
 // the launcher takes it from the stream-ordered allocator (cudaMallocAsync) for the duration of the launch.
@@ -148,6 +151,7 @@ __device__ __forceinline__ unsigned long long trace_now() { unsigned long long t
 
 constexpr unsigned look_back_rows   = GIDDY_DELTA_LOOK_BACK_ROWS;
 constexpr unsigned look_back_window = GIDDY_DELTA_LOOK_BACK_WINDOW; // descriptors per lane per round
+constexpr unsigned look_back_stages = GIDDY_DELTA_LOOK_BACK_STAGES; // tiles of deltas staged in shared memory
 
 struct alignas(16) tile_descriptor_t { unsigned long long word[2]; };
 enum : uint32_t { tile_unknown = 0, tile_has_aggregate = 1, tile_has_inclusive = 2 };
@@ -252,15 +256,80 @@ __device__ __forceinline__ uint_t<U> look_back(const tile_descriptor_t* descript
 	}
 }
 
-// Static == true : CTA b decodes tiles b, b + gridDim.x, ... -- needs every CTA of the grid resident at once (a
-//                   cooperative launch guarantees it), so that no tile waits for one whose CTA has not started.  The
-//                   order being known, the next tile's deltas are requested before this tile's look-back begins.
-// Static == false: tiles are drawn from a ticket counter, in order, so that every tile's predecessors are running or
-//                   done whatever the grid -- the fall-back where a cooperative launch is not to be had.  (Drawing
-//                   tickets ahead of time is not an option: a drawn but unstarted tile stalls all its successors,
-//                   and the stalls chain up -- measured 20x slower.)
-template <unsigned U, unsigned C, unsigned E, unsigned Rows, bool Static>
-__device__ __forceinline__ void decode_tiles_with_look_back(
+// How a column is cut into tiles (tiles never straddle segments: a segment's last tile may be ragged).
+struct tile_t { uint64_t segment, tile_in_segment, start, length; };
+
+struct tiling_t {
+	uint64_t length, segment_length, tile_elements, tiles_per_segment, num_tiles;
+
+	__device__ __forceinline__ tiling_t(uint64_t length_, uint64_t segment_length_, uint64_t tile_elements_) :
+		length(length_), segment_length(segment_length_), tile_elements(tile_elements_)
+	{
+		tiles_per_segment = (segment_length + tile_elements - 1) / tile_elements;
+		const uint64_t num_segments = (length + segment_length - 1) / segment_length;
+		const uint64_t last_segment_length = length - (num_segments - 1) * segment_length;
+		num_tiles = (num_segments - 1) * tiles_per_segment + (last_segment_length + tile_elements - 1) / tile_elements;
+	}
+
+	__device__ __forceinline__ tile_t locate(uint64_t tile) const
+	{
+		tile_t g;
+		g.segment = tile / tiles_per_segment;
+		g.tile_in_segment = tile - g.segment * tiles_per_segment;
+		const uint64_t segment_start = g.segment * segment_length;
+		const uint64_t offset = g.tile_in_segment * tile_elements;
+		g.start = segment_start + offset;
+		g.length = minimum(tile_elements, minimum(segment_length, length - segment_start) - offset);
+		return g;
+	}
+};
+
+// A warp scans its Rows rows of a tile (a lane's piece of a row: E deltas, the warp's rows start `warp_offset` elements
+// into the tile) onto `carry` -- the sum of everything before them -- and stores the results.
+// (`piece(r)`: the lane's E deltas of row r, as a byte_pack<E * C>)
+template <unsigned U, unsigned C, unsigned E, unsigned Rows, typename Piece>
+__device__ __forceinline__ void scan_and_store(
+	uint_t<U>* __restrict__ decompressed, Piece piece, const tile_t& g, uint64_t warp_offset, uint_t<U> carry)
+{
+	constexpr unsigned row_elements = warp_size * E;
+	#pragma unroll
+	for (unsigned r = 0; r < Rows; r++) {
+		const uint64_t p = warp_offset + r * row_elements + lane_index() * E;
+		const byte_pack<E * C> deltas = piece(r);
+		uint_t<U> local[E];
+		uint_t<U> sum = 0;
+		#pragma unroll
+		for (unsigned j = 0; j < E; j++) {
+			sum = (uint_t<U>)(sum + (uint_t<U>) deltas.template get<C>(j));
+			local[j] = sum;
+		}
+		const uint_t<U> inclusive = warp_inclusive_sum(sum);
+		const uint_t<U> before = (uint_t<U>)(carry + (uint_t<U>)(inclusive - sum));
+		carry = (uint_t<U>)(carry + shuffle_from(inclusive, warp_size - 1));
+		if (E > 1 && p + E <= g.length) {
+			byte_pack<E * U> vec; // 16 bytes, or a multiple of 32: 256-bit stores
+			#pragma unroll
+			for (unsigned j = 0; j < E; j++) { vec.template set<U>(j, (uint_t<U>)(before + local[j])); }
+			if constexpr (E * U >= 32) {
+				#pragma unroll
+				for (unsigned b = 0; b < E * U / 32; b++) {
+					store_streaming_32(reinterpret_cast<unsigned char*>(decompressed + g.start + p) + 32 * b, *reinterpret_cast<const uint32_t (*)[8]>(&vec.u32[8 * b]));
+				}
+			}
+			else { store_streaming_16(decompressed + g.start + p, make_uint4(vec.u32[0], vec.u32[1], vec.u32[2], vec.u32[3])); }
+		}
+		else {
+			#pragma unroll
+			for (unsigned j = 0; j < E; j++) { if (p + j < g.length) { decompressed[g.start + p + j] = (uint_t<U>)(before + local[j]); } }
+		}
+	}
+}
+
+// One tile at a time, its deltas in registers: load, reduce, barrier, look back (warp 0), barrier, scan and store.  Tiles are
+// drawn from the ticket counter, in order, so a tile's predecessors are running or done whatever the grid: the kernel for
+// columns too little aligned for bulk copies, and the fall-back where a cooperative launch is not to be had.
+template <unsigned U, unsigned C, unsigned E, unsigned Rows>
+__device__ __forceinline__ void decode_tiles_one_at_a_time(
 	uint_t<U>*        __restrict__  decompressed,
 	const uint_t<C>*  __restrict__  compressed_input,
 	const uint_t<U>*  __restrict__  anchor_values,
@@ -275,40 +344,28 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 
 	const unsigned lane = lane_index(), warp = warp_index_in_block(), num_warps = warps_per_block();
 	constexpr unsigned row_elements = warp_size * E;
-	const uint64_t tile_elements = (uint64_t) num_warps * Rows * row_elements;
-	const uint64_t tiles_per_segment = (segment_length + tile_elements - 1) / tile_elements;
-	const uint64_t num_segments = (length + segment_length - 1) / segment_length;
-	const uint64_t last_segment_length = length - (num_segments - 1) * segment_length;
-	const uint64_t num_tiles = (num_segments - 1) * tiles_per_segment + (last_segment_length + tile_elements - 1) / tile_elements;
+	const tiling_t tiling(length, segment_length, (uint64_t) num_warps * Rows * row_elements);
 	unsigned long long* const ticket_counter = static_cast<unsigned long long*>(workspace);
 	tile_descriptor_t* const descriptors = reinterpret_cast<tile_descriptor_t*>(static_cast<unsigned char*>(workspace) + 32);
-	const uint64_t warp_offset = (uint64_t) warp * Rows * row_elements + lane * E;
+	const uint64_t warp_offset = (uint64_t) warp * Rows * row_elements;
 
-	struct geometry_t { uint64_t segment, tile_in_segment, start, length; };
-	auto locate = [&](uint64_t tile) {
-		geometry_t g;
-		g.segment = tile / tiles_per_segment;
-		g.tile_in_segment = tile - g.segment * tiles_per_segment;
-		const uint64_t segment_start = g.segment * segment_length;
-		const uint64_t offset = g.tile_in_segment * tile_elements;
-		g.start = segment_start + offset;
-		g.length = minimum(tile_elements, minimum(segment_length, length - segment_start) - offset);
-		return g;
-	};
-	auto request = [&](byte_pack<E * C> (&deltas)[Rows], const geometry_t& g) {
+	if (threadIdx.x == 0) { shared_ticket[0] = atomicAdd(ticket_counter, 1ull); }
+	__syncthreads();
+	for (unsigned parity = 0; ; parity ^= 1u) {
+		const uint64_t tile = shared_ticket[parity];
+		if (tile >= tiling.num_tiles) { return; }
+		const tile_t g = tiling.locate(tile);
+		byte_pack<E * C> deltas[Rows];
 		#pragma unroll
 		for (unsigned r = 0; r < Rows; r++) {
-			const uint64_t p = warp_offset + r * row_elements;
+			const uint64_t p = warp_offset + r * row_elements + lane * E;
 			if (p + E <= g.length) { deltas[r] = load_pack<E * C>(compressed_input + g.start + p); }
 			else {
 				#pragma unroll
 				for (unsigned j = 0; j < E; j++) { deltas[r].template set<C>(j, (p + j < g.length) ? compressed_input[g.start + p + j] : (uint_t<C>) 0); }
 			}
 		}
-	};
-	// the warp's total first (one reduction): the tile's aggregate is published as early as possible and nothing but
-	// the deltas stays in registers across the look-back; the scans proper come afterwards
-	auto publish_warp_total = [&](const byte_pack<E * C> (&deltas)[Rows], unsigned parity) {
+		// the warp's total first (one reduction): the tile's aggregate is published as early as possible
 		uint_t<U> lane_total = 0;
 		#pragma unroll
 		for (unsigned r = 0; r < Rows; r++) {
@@ -317,16 +374,14 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 		}
 		const uint_t<U> warp_total = warp_sum(lane_total);
 		if (lane == 0) { warp_totals[parity][warp] = warp_total; }
-	};
-	// after the barrier: warp 0 settles the tile's exclusive prefix; returns what precedes this warp inside the tile
-	auto settle_prefix = [&](uint64_t tile, const geometry_t& g, unsigned parity) {
+		__syncthreads();
 		uint_t<U> preceding_warps = 0, tile_aggregate = 0;
 		for (unsigned w = 0; w < num_warps; w++) {
 			const uint_t<U> t = warp_totals[parity][w];
 			if (w < warp) { preceding_warps = (uint_t<U>)(preceding_warps + t); }
 			tile_aggregate = (uint_t<U>)(tile_aggregate + t);
 		}
-		if (warp == 0) {
+		if (warp == 0) { // settles the tile's exclusive prefix
 			tile_descriptor_t* mine = descriptors + tile;
 			uint_t<U> exclusive;
 			if (g.tile_in_segment == 0) { exclusive = __ldg(anchor_values + g.segment); }
@@ -337,137 +392,185 @@ __device__ __forceinline__ void decode_tiles_with_look_back(
 			if (lane == 0) {
 				publish<U>(mine, tile_has_inclusive, (uint_t<U>)(exclusive + tile_aggregate));
 				shared_tile_exclusive[parity] = exclusive;
-				if (!Static) { shared_ticket[parity ^ 1u] = atomicAdd(ticket_counter, 1ull); }
+				shared_ticket[parity ^ 1u] = atomicAdd(ticket_counter, 1ull);
 			}
 		}
-		return preceding_warps;
+		__syncthreads();
+		scan_and_store<U, C, E, Rows>(decompressed, [&](unsigned r) { return deltas[r]; }, g, warp_offset, (uint_t<U>)(shared_tile_exclusive[parity] + preceding_warps));
+	}
+}
+
+// Cooperative launch, statically assigned tiles, deltas staged in shared memory by TMA: a warp owns a contiguous chunk of
+// every tile (Rows x 512 bytes of deltas) and fetches it with ONE bulk copy (cp.async.bulk, SASS UBLKCP) completing on its
+// own mbarrier, `look_back_stages` tiles ahead -- the copy of tile k + stages is issued as soon as the warp has read tile
+// k's chunk into registers.  So a CTA has loads in flight during its scan-and-store phases too, nothing but one tile's
+// deltas is ever held in registers (no spills), and a tile's loads are one request per warp instead of Rows per thread.
+//
+// Software pipeline, one CTA barrier per tile.  While warp 0 looks back for tile k, the other warps reduce tile k+1's
+// staged deltas; after the barrier tile k+1's aggregate is published -- a whole scan-and-store phase before its own
+// look-back begins -- and only then tile k is scanned and stored.
+//
+// Requires the alignment of the wide-piece shape: 16 bytes of deltas per lane and row (E * C == 16).
+// Dynamic shared memory: look_back_stages x (the tile's deltas) = GIDDY_DELTA_LOOK_BACK_SHARED_BYTES.
+template <unsigned U, unsigned C, unsigned E, unsigned Rows>
+__device__ __forceinline__ void decode_tiles_staged(
+	uint_t<U>*        __restrict__  decompressed,
+	const uint_t<C>*  __restrict__  compressed_input,
+	const uint_t<U>*  __restrict__  anchor_values,
+	uint64_t                        length,
+	uint64_t                        segment_length,
+	void*                           workspace)
+{
+	static_assert(E * C == 16, "a lane's piece of a row is one 16-byte vector of deltas");
+	constexpr unsigned stages = look_back_stages;
+	extern __shared__ __align__(128) unsigned char staged_deltas[]; // [stages][warps of the CTA][Rows][32 lanes] x 16 bytes
+	__shared__ uint_t<U> totals[3][32];          // [tile ordinal % 3][warp]: written an iteration ahead, read in two iterations
+	__shared__ uint_t<U> exclusives[2];
+	__shared__ uint64_t  arrived[stages][32];    // [stage][warp]: the mbarrier a warp's chunk completes on
+
+	const unsigned lane = lane_index(), warp = warp_index_in_block(), num_warps = warps_per_block();
+	constexpr unsigned row_elements = warp_size * E;
+	constexpr unsigned chunk_elements = Rows * row_elements;
+	constexpr unsigned chunk_bytes = chunk_elements * C;
+	const tiling_t tiling(length, segment_length, (uint64_t) num_warps * chunk_elements);
+	tile_descriptor_t* const descriptors = reinterpret_cast<tile_descriptor_t*>(static_cast<unsigned char*>(workspace) + 32);
+	const uint64_t warp_offset = (uint64_t) warp * chunk_elements;
+
+	auto chunk = [&](unsigned stage) { return staged_deltas + ((size_t) stage * num_warps + warp) * chunk_bytes; };
+	// the whole warp calls this, having finished with whatever the stage held before
+	auto request = [&](const tile_t& g, unsigned stage) {
+		const uint64_t available = g.length > warp_offset ? minimum<uint64_t>(g.length - warp_offset, chunk_elements) : 0;
+		if (available == chunk_elements) {
+			if (lane == 0) {
+				fence_proxy_async_shared();
+				mbarrier_expect_bytes(&arrived[stage][warp], chunk_bytes);
+				tma_bulk_load(chunk(stage), compressed_input + g.start + warp_offset, chunk_bytes, &arrived[stage][warp]);
+			}
+		}
+		else { // a segment's last, ragged tile: element by element, zero-filled
+			uint_t<C>* const destination = reinterpret_cast<uint_t<C>*>(chunk(stage));
+			for (unsigned i = lane; i < chunk_elements; i += warp_size) {
+				destination[i] = (i < available) ? compressed_input[g.start + warp_offset + i] : (uint_t<C>) 0;
+			}
+			__syncwarp();
+			if (lane == 0) { mbarrier_arrive(&arrived[stage][warp]); }
+		}
 	};
-	auto scan_and_store = [&](const byte_pack<E * C> (&deltas)[Rows], const geometry_t& g, uint_t<U> carry) {
+	auto staged_piece = [&](unsigned stage, unsigned r) {
+		const uint4 t = *reinterpret_cast<const uint4*>(chunk(stage) + ((size_t) r * warp_size + lane) * 16);
+		byte_pack<16> v;
+		v.u32[0] = t.x; v.u32[1] = t.y; v.u32[2] = t.z; v.u32[3] = t.w;
+		return v;
+	};
+	auto publish_totals = [&](unsigned stage, unsigned slot) {
+		uint_t<U> lane_total = 0;
 		#pragma unroll
 		for (unsigned r = 0; r < Rows; r++) {
-			const uint64_t p = warp_offset + r * row_elements;
-			uint_t<U> local[E];
-			uint_t<U> sum = 0;
+			const byte_pack<16> v = staged_piece(stage, r);
 			#pragma unroll
-			for (unsigned j = 0; j < E; j++) {
-				sum = (uint_t<U>)(sum + (uint_t<U>) deltas[r].template get<C>(j));
-				local[j] = sum;
-			}
-			const uint_t<U> inclusive = warp_inclusive_sum(sum);
-			const uint_t<U> before = (uint_t<U>)(carry + (uint_t<U>)(inclusive - sum));
-			carry = (uint_t<U>)(carry + shuffle_from(inclusive, warp_size - 1));
-			if (E > 1 && p + E <= g.length) {
-				byte_pack<E * U> vec; // 16 bytes, or a multiple of 32: 256-bit stores
-				#pragma unroll
-				for (unsigned j = 0; j < E; j++) { vec.template set<U>(j, (uint_t<U>)(before + local[j])); }
-				if constexpr (E * U >= 32) {
-					#pragma unroll
-					for (unsigned b = 0; b < E * U / 32; b++) {
-						store_streaming_32(reinterpret_cast<unsigned char*>(decompressed + g.start + p) + 32 * b, *reinterpret_cast<const uint32_t (*)[8]>(&vec.u32[8 * b]));
-					}
-				}
-				else { store_streaming_16(decompressed + g.start + p, make_uint4(vec.u32[0], vec.u32[1], vec.u32[2], vec.u32[3])); }
-			}
-			else {
-				#pragma unroll
-				for (unsigned j = 0; j < E; j++) { if (p + j < g.length) { decompressed[g.start + p + j] = (uint_t<U>)(before + local[j]); } }
-			}
+			for (unsigned j = 0; j < E; j++) { lane_total = (uint_t<U>)(lane_total + (uint_t<U>) v.template get<C>(j)); }
 		}
+		const uint_t<U> warp_total = warp_sum(lane_total);
+		if (lane == 0) { totals[slot][warp] = warp_total; }
+	};
+	// thread 0, after the barrier: the tile's aggregate -- or, for a segment's first tile, already its inclusive prefix
+	auto publish_early = [&](uint64_t tile, const tile_t& g, unsigned slot) {
+		uint_t<U> aggregate = 0;
+		for (unsigned w = 0; w < num_warps; w++) { aggregate = (uint_t<U>)(aggregate + totals[slot][w]); }
+		if (g.tile_in_segment == 0) { publish<U>(descriptors + tile, tile_has_inclusive, (uint_t<U>)(__ldg(anchor_values + g.segment) + aggregate)); }
+		else { publish<U>(descriptors + tile, tile_has_aggregate, aggregate); }
 	};
 
-	if (Static) {
-		// Software pipeline, one barrier per tile.  While warp 0 looks back for tile k, the other warps wait for tile
-		// k+1's deltas (requested at the top of the iteration) and reduce them; after the barrier tile k+1's aggregate
-		// is published -- a whole scan-and-store phase before its own look-back begins, so that by then the
-		// neighbouring CTAs' aggregates are normally there and look-backs rarely have to poll twice -- and only
-		// then tile k is scanned and stored.
-		__shared__ uint_t<U> totals[3][32];   // [tile ordinal % 3]: written an iteration ahead, read in two iterations
-		__shared__ uint_t<U> exclusives[2];
-		auto publish_totals = [&](const byte_pack<E * C> (&deltas)[Rows], unsigned slot) {
-			uint_t<U> lane_total = 0;
-			#pragma unroll
-			for (unsigned r = 0; r < Rows; r++) {
-				#pragma unroll
-				for (unsigned j = 0; j < E; j++) { lane_total = (uint_t<U>)(lane_total + (uint_t<U>) deltas[r].template get<C>(j)); }
-			}
-			const uint_t<U> warp_total = warp_sum(lane_total);
-			if (lane == 0) { totals[slot][warp] = warp_total; }
-		};
-		// thread 0, after the barrier: the tile's aggregate -- or, for a segment's first tile, already its inclusive prefix
-		auto publish_early = [&](uint64_t tile, const geometry_t& g, unsigned slot) {
-			uint_t<U> aggregate = 0;
-			for (unsigned w = 0; w < num_warps; w++) { aggregate = (uint_t<U>)(aggregate + totals[slot][w]); }
-			if (g.tile_in_segment == 0) { publish<U>(descriptors + tile, tile_has_inclusive, (uint_t<U>)(__ldg(anchor_values + g.segment) + aggregate)); }
-			else { publish<U>(descriptors + tile, tile_has_aggregate, aggregate); }
-		};
-
-		uint64_t tile = blockIdx.x;
-		if (tile >= num_tiles) { return; }
-		geometry_t g = locate(tile);
-		byte_pack<E * C> deltas[Rows], next_deltas[Rows];
-		request(deltas, g);
-		publish_totals(deltas, 0);
-		__syncthreads();
-		if (threadIdx.x == 0) { publish_early(tile, g, 0); }
-
-		for (unsigned ordinal = 0; ; ordinal++) {
-			const unsigned slot = ordinal % 3, next_slot = (ordinal + 1) % 3, parity = ordinal & 1u;
-			const uint64_t next_tile = tile + gridDim.x;
-			const bool has_next = next_tile < num_tiles;
-			geometry_t next_g = g;
-			GIDDY_DELTA_TRACE_POINT(tile, 0);
-			if (has_next) { next_g = locate(next_tile); request(next_deltas, next_g); }
-			if (warp == 0) {
-				uint_t<U> exclusive;
-				if (g.tile_in_segment == 0) { exclusive = __ldg(anchor_values + g.segment); }
-				else {
-					exclusive = look_back<U>(descriptors, tile, g.tile_in_segment);
-					if (lane == 0) {
-						uint_t<U> aggregate = 0;
-						for (unsigned w = 0; w < num_warps; w++) { aggregate = (uint_t<U>)(aggregate + totals[slot][w]); }
-						publish<U>(descriptors + tile, tile_has_inclusive, (uint_t<U>)(exclusive + aggregate));
-					}
-				}
-				if (lane == 0) { exclusives[parity] = exclusive; }
-			}
-			GIDDY_DELTA_TRACE_POINT(tile, 1);
-			if (has_next) { publish_totals(next_deltas, next_slot); }
-			GIDDY_DELTA_TRACE_POINT(tile, 2);
-			__syncthreads();
-			GIDDY_DELTA_TRACE_POINT(tile, 3);
-			if (has_next && threadIdx.x == 0) { publish_early(next_tile, next_g, next_slot); }
-			GIDDY_DELTA_TRACE_POINT(tile, 4);
-			uint_t<U> carry = exclusives[parity];
-			for (unsigned w = 0; w < warp; w++) { carry = (uint_t<U>)(carry + totals[slot][w]); }
-			scan_and_store(deltas, g, carry);
-			GIDDY_DELTA_TRACE_POINT(tile, 5);
-			if (!has_next) { return; }
-			#pragma unroll
-			for (unsigned r = 0; r < Rows; r++) { deltas[r] = next_deltas[r]; }
-			tile = next_tile; g = next_g;
-		}
+	uint64_t tile = blockIdx.x;
+	if (tile >= tiling.num_tiles) { return; }
+	if (lane == 0) {
+		#pragma unroll
+		for (unsigned s = 0; s < stages; s++) { mbarrier_init(&arrived[s][warp], 1); }
 	}
-	else {
-		if (threadIdx.x == 0) { shared_ticket[0] = atomicAdd(ticket_counter, 1ull); }
-		__syncthreads();
-		for (unsigned parity = 0; ; parity ^= 1u) {
-			const uint64_t tile = shared_ticket[parity];
-			if (tile >= num_tiles) { return; }
-			const geometry_t g = locate(tile);
-			byte_pack<E * C> deltas[Rows];
-			request(deltas, g);
-			publish_warp_total(deltas, parity);
-			__syncthreads();
-			const uint_t<U> preceding_warps = settle_prefix(tile, g, parity);
-			__syncthreads();
-			scan_and_store(deltas, g, (uint_t<U>)(shared_tile_exclusive[parity] + preceding_warps));
+	__syncwarp();
+	tile_t g = tiling.locate(tile);
+	#pragma unroll
+	for (unsigned s = 0; s < stages; s++) {
+		const uint64_t ahead = tile + (uint64_t) s * gridDim.x;
+		if (ahead < tiling.num_tiles) { request(tiling.locate(ahead), s); }
+	}
+	mbarrier_wait(&arrived[0][warp], 0);
+	publish_totals(0, 0);
+	__syncthreads();
+	if (threadIdx.x == 0) { publish_early(tile, g, 0); }
+
+	for (unsigned ordinal = 0; ; ordinal++) {
+		const unsigned slot = ordinal % 3, next_slot = (ordinal + 1) % 3, parity = ordinal & 1u;
+		const unsigned stage = ordinal % stages, next_stage = (ordinal + 1) % stages;
+		const uint64_t next_tile = tile + gridDim.x;
+		const bool has_next = next_tile < tiling.num_tiles;
+		tile_t next_g = g;
+		if (has_next) { next_g = tiling.locate(next_tile); }
+		GIDDY_DELTA_TRACE_POINT(tile, 0);
+		if (warp == 0) {
+			uint_t<U> exclusive;
+			if (g.tile_in_segment == 0) { exclusive = __ldg(anchor_values + g.segment); }
+			else {
+				exclusive = look_back<U>(descriptors, tile, g.tile_in_segment);
+				if (lane == 0) {
+					uint_t<U> aggregate = 0;
+					for (unsigned w = 0; w < num_warps; w++) { aggregate = (uint_t<U>)(aggregate + totals[slot][w]); }
+					publish<U>(descriptors + tile, tile_has_inclusive, (uint_t<U>)(exclusive + aggregate));
+				}
+			}
+			if (lane == 0) { exclusives[parity] = exclusive; }
 		}
+		GIDDY_DELTA_TRACE_POINT(tile, 1);
+		if (has_next) {
+			mbarrier_wait(&arrived[next_stage][warp], ((ordinal + 1) / stages) & 1u);
+			publish_totals(next_stage, next_slot);
+		}
+		GIDDY_DELTA_TRACE_POINT(tile, 2);
+		__syncthreads();
+		GIDDY_DELTA_TRACE_POINT(tile, 3);
+		if (has_next && threadIdx.x == 0) { publish_early(next_tile, next_g, next_slot); }
+		GIDDY_DELTA_TRACE_POINT(tile, 4);
+		uint_t<U> carry = exclusives[parity];
+		for (unsigned w = 0; w < warp; w++) { carry = (uint_t<U>)(carry + totals[slot][w]); }
+		// this tile's deltas: shared memory -> registers, which frees the stage for the tile `stages` ahead
+		byte_pack<16> deltas[Rows];
+		#pragma unroll
+		for (unsigned r = 0; r < Rows; r++) { deltas[r] = staged_piece(stage, r); }
+		__syncwarp();
+		const uint64_t ahead = tile + (uint64_t) stages * gridDim.x;
+		if (ahead < tiling.num_tiles) { request(tiling.locate(ahead), stage); }
+		scan_and_store<U, C, E, Rows>(decompressed, [&](unsigned r) { return deltas[r]; }, g, warp_offset, carry);
+		GIDDY_DELTA_TRACE_POINT(tile, 5);
+		if (!has_next) { return; }
+		tile = next_tile; g = next_g;
 	}
 }
 
 } // namespace delta_detail
 
-template <unsigned IndexSize, unsigned U, unsigned C, bool Static>
+// A lane's piece of a row is "wide" where alignment allows -- at least 32 output bytes (256-bit stores) and a whole 16-byte
+// vector of deltas: half (or less) the load, store and shuffle instructions per byte -- else 16 output bytes, else one
+// element; a tile holds the same number of elements in all three shapes.
+template <unsigned U, unsigned C>
+struct look_back_shapes {
+	static constexpr unsigned E = 16 / U;
+	static constexpr unsigned rows = delta_detail::look_back_rows;
+	static constexpr unsigned wide = (16 / C > 2 * E) ? 16 / C : 2 * E; // elements of a wide piece
+	static constexpr unsigned wide_rows = rows * E / wide;
+	static_assert((rows * E) % wide == 0, "a tile is also cut into rows of wide pieces");
+
+	static __host__ __device__ bool vectorizable(const void* decompressed, const void* compressed_input, uint64_t segment_length)
+	{
+		return reinterpret_cast<uintptr_t>(decompressed) % 16 == 0 && reinterpret_cast<uintptr_t>(compressed_input) % (E * C) == 0 && segment_length % E == 0;
+	}
+	static __host__ __device__ bool wide_pieces(const void* decompressed, const void* compressed_input, uint64_t segment_length)
+	{
+		return reinterpret_cast<uintptr_t>(decompressed) % 32 == 0 && reinterpret_cast<uintptr_t>(compressed_input) % (wide * C) == 0 && segment_length % wide == 0;
+	}
+};
+
+// Any grid; workspace as above.
+template <unsigned IndexSize, unsigned U, unsigned C>
 __global__ void __launch_bounds__(GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS, GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR)
 delta_decompress_long_segments(
 	uint_t<U>*        __restrict__  decompressed,
@@ -477,19 +580,32 @@ delta_decompress_long_segments(
 	size_type<IndexSize>            segment_length,
 	void*                           workspace)
 {
-	constexpr unsigned E = 16 / U;
-	const bool vectorizable = is_aligned_to(decompressed, 16) && is_aligned_to(compressed_input, E * C) && (segment_length % E == 0);
-	// (a lane's piece of a row is 32 output bytes where alignment allows -- half the load, store and shuffle instructions
-	// per byte: the kernel is bound by the requests a multiprocessor can keep in flight -- else 16, else one element; the
-	// tile holds the same number of elements in the two vector shapes)
-	// (wide pieces: at least 32 output bytes and, where the deltas are narrow, a whole 16-byte load of them)
-	constexpr unsigned rows = delta_detail::look_back_rows;
-	constexpr unsigned wide = (16 / C > 2 * E) ? 16 / C : 2 * E; // elements of a wide piece
-	static_assert((rows * E) % wide == 0, "a tile is also cut into rows of wide pieces");
-	const bool vectorizable_32 = vectorizable && is_aligned_to(decompressed, 32) && is_aligned_to(compressed_input, wide * C) && (segment_length % wide == 0);
-	if (vectorizable_32)   { delta_detail::decode_tiles_with_look_back<U, C, wide, rows * E / wide, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
-	else if (vectorizable) { delta_detail::decode_tiles_with_look_back<U, C, E, rows, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
-	else                   { delta_detail::decode_tiles_with_look_back<U, C, 1, rows, Static>(decompressed, compressed_input, anchor_values, length, segment_length, workspace); }
+	using shapes = look_back_shapes<U, C>;
+	if (shapes::wide_pieces(decompressed, compressed_input, segment_length)) {
+		delta_detail::decode_tiles_one_at_a_time<U, C, shapes::wide, shapes::wide_rows>(decompressed, compressed_input, anchor_values, length, segment_length, workspace);
+	}
+	else if (shapes::vectorizable(decompressed, compressed_input, segment_length)) {
+		delta_detail::decode_tiles_one_at_a_time<U, C, shapes::E, shapes::rows>(decompressed, compressed_input, anchor_values, length, segment_length, workspace);
+	}
+	else {
+		delta_detail::decode_tiles_one_at_a_time<U, C, 1, shapes::rows>(decompressed, compressed_input, anchor_values, length, segment_length, workspace);
+	}
+}
+
+// Columns aligned for wide pieces (look_back_shapes::wide_pieces -- the launcher checks) only; to be launched cooperatively,
+// with at most as many CTAs as are resident at once and GIDDY_DELTA_LOOK_BACK_SHARED_BYTES of dynamic shared memory.
+template <unsigned IndexSize, unsigned U, unsigned C>
+__global__ void __launch_bounds__(GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS, GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR)
+delta_decompress_long_segments_staged(
+	uint_t<U>*        __restrict__  decompressed,
+	const uint_t<C>*  __restrict__  compressed_input,
+	const uint_t<U>*  __restrict__  anchor_values,
+	size_type<IndexSize>            length,
+	size_type<IndexSize>            segment_length,
+	void*                           workspace)
+{
+	using shapes = look_back_shapes<U, C>;
+	delta_detail::decode_tiles_staged<U, C, shapes::wide, shapes::wide_rows>(decompressed, compressed_input, anchor_values, length, segment_length, workspace);
 }
 
 } // namespace kernels

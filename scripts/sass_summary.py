@@ -24,7 +24,7 @@ PATTERNS = [
 HEADLINE = [
     "frame_of_reference_decompress<4, 4, 2, 0, 4>", "frame_of_reference_decompress<4, 4, 2, 1, 4>",
     "run_length_encoding_decompress<4, 4, 2, 4>", "run_position_encoding_decompress<4, 4, 4, false, 4>",
-    "delta_decompress<4, 8, 4>", "delta_decompress_long_segments<4, 8, 4, true>", "dictionary_decompress<4, 8, 1>",
+    "delta_decompress<4, 8, 4>", "delta_decompress_long_segments_staged<4, 8, 4>", "delta_decompress_long_segments<4, 8, 4>", "dictionary_decompress<4, 8, 1>",
     "discard_zero_bytes_variable_decompress<4, 4, 4>", "delta_of_discard_zero_bytes_variable_decompress<4, 8, 4, 4>",
     "incidence_bitmaps_decompress<4, 4, 2, true>", "scatter<4, 8, 4>", "compressed_indices_scatter<4, 4, 4, 4>",
     "patched_dictionary_decompress<4, 8, 1>", "patched_frame_of_reference_decompress<4, 4, 2, 1, 4>", "expand_compressed_indices<4, 4, 4>", "patched_detail::patch_tile_ranges<4>",

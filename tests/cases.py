@@ -459,6 +459,7 @@ def all_cases():
     cases.append(delta_case(12, (1 << 22) + 5, 1 << 21, 8, 2))
     cases.append(delta_case(13, (1 << 23) + 77, 1 << 23, 4, 1))             # > 1000 tiles in one segment: look-backs of several rounds
     cases.append(delta_case(14, 3 * 24576 + 100, 24576, 8, 4))              # the shortest segments which take the look-back path
+    cases.append(delta_case(15, 700000 + 1, 200002, 8, 4))                  # L a multiple of the 16-byte vector but not of a wide piece: no bulk copies
     # Dictionary (20 keys)
     for I in (4, 8):
         for (U, DI) in [(1, 1), (2, 1), (2, 2), (4, 1), (4, 2), (4, 4), (8, 1), (8, 2), (8, 4), (8, 8)]:
