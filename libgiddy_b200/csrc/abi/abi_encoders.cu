@@ -87,8 +87,28 @@ struct for_entry_t { unsigned I, U, C; int model; const void* kernel; for_launch
 template <unsigned I, unsigned U, unsigned C, int M>
 giddy_status_t for_launch(void* stream, const giddy_launch_config_t* cfg, void* compressed, void* coefficients, const void* in, uint64_t n, uint64_t L, unsigned* status)
 {
-	return launch(enc::frame_of_reference_compress<I, U, C, M>, stream, cfg, static_cast<int_t<C>*>(compressed), static_cast<int32_t*>(coefficients),
-		static_cast<const int_t<U>*>(in), (size_type<I>) n, (size_type<I>) L, status);
+	constexpr unsigned E = 16 / U, dim = (M == model_linear) ? 2 : 1;
+	auto out = static_cast<int_t<C>*>(compressed);
+	auto coefficients_ = static_cast<int32_t*>(coefficients);
+	auto x = static_cast<const int_t<U>*>(in);
+	// Segments of a few KB to a few tens of KB, aligned: a CTA per segment holds it in registers between the fit and the store
+	// (one read of the column); a short last segment goes through the general kernel.
+	const uint64_t vectors = L / E, whole_segments = L ? n / L : 0;
+	const bool by_block = L % E == 0 && vectors > enc::for_block_threads && vectors <= (uint64_t) enc::for_block_threads * enc::for_block_vectors &&
+		reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(compressed) % (E * C) == 0 && whole_segments > 0 &&
+		cfg->grid_dimensions[0] != 0 && cfg->block_dimensions[0] != 0;
+	if (!by_block) {
+		return launch(enc::frame_of_reference_compress<I, U, C, M>, stream, cfg, out, coefficients_, x, (size_type<I>) n, (size_type<I>) L, status);
+	}
+	const unsigned blocks = helper_blocks(whole_segments, 1);
+	enc::frame_of_reference_compress_by_block<I, U, C, M><<<blocks, enc::for_block_threads, 0, as_stream(stream)>>>(out, coefficients_, x,
+		(size_type<I>)(whole_segments * L), (size_type<I>) L, status);
+	giddy_status_t result = launched("kernel launch (frame of reference, a block per segment)");
+	if (result != GIDDY_SUCCESS || whole_segments * L == n) { return result; }
+	giddy_launch_config_t one_warp = *cfg;
+	one_warp.grid_dimensions[0] = 1; one_warp.block_dimensions[0] = 32;
+	return launch(enc::frame_of_reference_compress<I, U, C, M>, stream, &one_warp, out + whole_segments * L, coefficients_ + whole_segments * dim,
+		x + whole_segments * L, (size_type<I>)(n - whole_segments * L), (size_type<I>) L, status);
 }
 #define FOR_ENTRY(I, U, C, M) { I, U, C, M, reinterpret_cast<const void*>(&enc::frame_of_reference_compress<I, U, C, M>), &for_launch<I, U, C, M> }
 const for_entry_t for_table[] = {
@@ -253,9 +273,19 @@ giddy_status_t dzbv_launch(void* stream, const giddy_launch_config_t* cfg, void*
 	if (error != cudaSuccess) { return fail_cuda(error, "cudaMallocFromPoolAsync (variable-width encoder workspace)"); }
 	auto* segment_bytes = static_cast<uint64_t*>(workspace.memory);
 	const unsigned block = cfg->block_dimensions[0] ? cfg->block_dimensions[0] : 256;
-	const unsigned grid = cfg->grid_dimensions[0] ? cfg->grid_dimensions[0] : helper_blocks(num_segments, block / 32);
+	// (warps take segments grid-stride: more CTAs than fill the device a few times over only cost their launches)
+	const unsigned enough = helper_blocks(num_segments, block / 32);
+	const unsigned grid = (cfg->grid_dimensions[0] && cfg->grid_dimensions[0] < enough) ? cfg->grid_dimensions[0] : enough;
 	auto x = static_cast<const uint_t<U>*>(in);
-	enc::variable_width_segment_bytes<U><<<grid, block, 0, s>>>(segment_bytes, x, n, L, min_size, bits, status);
+	// the size containers come out of the first pass where they straddle neither a lane's 16-byte vector nor segments and are
+	// made of a power-of-two number of lanes' fields
+	constexpr unsigned E = 16 / U;
+	const unsigned per_container = (8 * CS) / bits;
+	const unsigned lanes_per_container = per_container / E; // (a power of two for 1, 2, 4 and 8-bit fields)
+	const bool pack_in_first_pass = reinterpret_cast<uintptr_t>(in) % 16 == 0 && L % E == 0 && per_container % E == 0 && L % per_container == 0 &&
+		lanes_per_container >= 1 && (lanes_per_container & (lanes_per_container - 1)) == 0;
+	enc::variable_width_sizes<U, CS><<<grid, block, 0, s>>>(segment_bytes, pack_in_first_pass ? static_cast<uint_t<CS>*>(packed) : nullptr,
+		x, n, L, min_size, bits, status);
 	giddy_status_t result = launched("kernel launch (variable-width segment sizes)");
 	if (result != GIDDY_SUCCESS) { return result; }
 	uint64_t* chunk_totals = segment_bytes + num_segments + 1;
@@ -263,10 +293,14 @@ giddy_status_t dzbv_launch(void* stream, const giddy_launch_config_t* cfg, void*
 	enc::run_scan_chunks<false><<<1, 1024, 0, s>>>(chunk_totals, num_chunks, chunk_totals + num_chunks);
 	enc::add_chunk_bases<<<(unsigned) num_chunks, enc::placement_chunk_tiles, 0, s>>>(segment_bytes, chunk_totals, chunk_totals + num_chunks, num_segments);
 	if ((result = launched("kernel launch (segment byte offsets)")) != GIDDY_SUCCESS) { return result; }
-	enc::variable_width_emit<I, U><<<grid, block, 0, s>>>(static_cast<uint8_t*>(data), static_cast<uint_t<I>*>(anchors), static_cast<uint64_t*>(num_bytes_out),
+	const unsigned windows = (block / 32) * enc::emit_window_bytes;
+	error = ensure_dynamic_shared_memory(reinterpret_cast<const void*>(&enc::variable_width_emit<I, U>), windows);
+	if (error != cudaSuccess) { return fail_cuda(error, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); }
+	enc::variable_width_emit<I, U><<<grid, block, windows, s>>>(static_cast<uint8_t*>(data), static_cast<uint_t<I>*>(anchors), static_cast<uint64_t*>(num_bytes_out),
 		x, segment_bytes, n, L, min_size, data_capacity, status);
 	if ((result = launched("kernel launch (variable-width emission)")) != GIDDY_SUCCESS) { return result; }
-	const uint64_t containers = (n + (8 * CS) / bits - 1) / ((8 * CS) / bits);
+	if (pack_in_first_pass) { return GIDDY_SUCCESS; }
+	const uint64_t containers = (n + per_container - 1) / per_container;
 	enc::variable_width_pack_sizes<U, CS><<<helper_blocks(containers, 256), 256, 0, s>>>(static_cast<uint_t<CS>*>(packed), x, n, min_size, bits);
 	return launched("kernel launch (size containers)");
 }

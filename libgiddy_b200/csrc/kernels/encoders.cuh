@@ -88,6 +88,8 @@ __device__ __forceinline__ void encode_elementwise(uint_t<C>* __restrict__ compr
 // Delta (format: reference src/kernels/decompression/delta.cuh:66-108):
 //   compressed[i] = x[i] - x[i-1] (mod 2^(8U); x[-1] = base), anchor_values[s] = x[s*L - 1] (base for s = 0)
 // -------------------------------------------------------------------------------------------------
+// The skeleton of encode_elementwise; the element before a lane's vector comes from the lane below by shuffle (lane 0 of a
+// warp loads it), so the column is read once.
 template <unsigned IndexSize, unsigned U, unsigned C>
 __global__ void delta_compress(
 	uint_t<C>*        __restrict__  compressed,
@@ -98,16 +100,57 @@ __global__ void delta_compress(
 	uint_t<U>                       base,
 	unsigned*                       status)
 {
+	constexpr unsigned E = 16 / U;
 	bool overflow = false;
-	encode_elementwise<U, C>(compressed, uncompressed, length, [&](uint64_t i, uint_t<U> x) {
-		const uint_t<U> previous = (i == 0) ? base : __ldg(uncompressed + i - 1);
+	auto encode = [&](uint_t<U> x, uint_t<U> previous) {
 		const uint_t<U> delta = (uint_t<U>)(x - previous);
 		if (C < U && (uint64_t) delta >> (8 * C) != 0) { overflow = true; }
 		return (uint_t<C>) delta;
-	});
+	};
+	const uint64_t global_thread = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t num_threads = (uint64_t) gridDim.x * blockDim.x;
+	const uint64_t n = length;
+	if (!(is_aligned_to(uncompressed, 16) && is_aligned_to(compressed, E * C)) || blockDim.x % warp_size != 0) {
+		for (uint64_t i = global_thread; i < n; i += num_threads) { compressed[i] = encode(uncompressed[i], (i == 0) ? base : uncompressed[i - 1]); }
+	}
+	else {
+		const uint64_t num_vectors = n / E;
+		const uint64_t vectors_per_tile = (uint64_t) blockDim.x * elementwise_unroll;
+		#pragma unroll 1
+		for (uint64_t tile_start = (uint64_t) blockIdx.x * vectors_per_tile; tile_start < num_vectors; tile_start += (uint64_t) gridDim.x * vectors_per_tile) {
+			byte_pack<16> in[elementwise_unroll];
+			uint_t<U> before[elementwise_unroll]; // lane 0: the element before the warp's vectors of step k
+			#pragma unroll
+			for (unsigned k = 0; k < elementwise_unroll; k++) {
+				const uint64_t v = tile_start + (uint64_t) k * blockDim.x + threadIdx.x;
+				if (v < num_vectors) { in[k] = load_pack<16>(uncompressed + v * E); }
+				before[k] = 0;
+				if (lane_index() == 0 && v < num_vectors) { before[k] = (v == 0) ? base : __ldg(uncompressed + v * E - 1); }
+			}
+			#pragma unroll
+			for (unsigned k = 0; k < elementwise_unroll; k++) {
+				const uint64_t v = tile_start + (uint64_t) k * blockDim.x + threadIdx.x;
+				// (the shuffle is executed by the whole warp; lanes past the end hold nothing anybody needs)
+				const uint_t<U> last = (v < num_vectors) ? in[k].template get<U>(E - 1) : (uint_t<U>) 0;
+				const uint_t<U> from_below = shuffle_up(last, 1);
+				if (v >= num_vectors) { continue; }
+				uint_t<U> previous = (lane_index() == 0) ? before[k] : from_below;
+				byte_pack<E * C> out;
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) {
+					const uint_t<U> x = in[k].template get<U>(j);
+					out.template set<C>(j, encode(x, previous));
+					previous = x;
+				}
+				store_pack<E * C>(compressed + v * E, out);
+			}
+		}
+		const uint64_t tail = num_vectors * E + global_thread;
+		if (tail < n) { compressed[tail] = encode(uncompressed[tail], (tail == 0) ? base : uncompressed[tail - 1]); }
+	}
 	if (overflow) { raise(status, status_unrepresentable); }
-	const uint64_t num_segments = ((uint64_t) length + segment_length - 1) / segment_length;
-	for (uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; s < num_segments; s += (uint64_t) gridDim.x * blockDim.x) {
+	const uint64_t num_segments = (n + segment_length - 1) / segment_length;
+	for (uint64_t s = global_thread; s < num_segments; s += num_threads) {
 		anchor_values[s] = (s == 0) ? base : __ldg(uncompressed + s * segment_length - 1);
 	}
 }
@@ -298,6 +341,88 @@ __global__ void frame_of_reference_compress(
 			const int64_t offset = (int64_t) x[i] - (c0 + c1 * (int64_t) i);
 			if (offset < lowest || offset > highest) { overflow = true; }
 			compressed[start + i] = (int_t<C>) offset;
+		}
+	}
+	if (overflow) { raise(status, status_unrepresentable); }
+}
+
+constexpr unsigned for_block_threads = 256;
+constexpr unsigned for_block_vectors = 8; // 16-byte vectors of a segment a thread holds
+
+// A CTA per segment, the segment's 16-byte vectors held in registers between the fit and the store: the column is read once
+// (frame_of_reference_compress reads a segment twice, the second time out of L2).  Whole segments only, of 16-byte aligned
+// columns, with at most for_block_threads x for_block_vectors vectors each (the launcher checks, and leaves a short last
+// segment to frame_of_reference_compress).
+template <unsigned IndexSize, unsigned U, unsigned C, int Model>
+__global__ void __launch_bounds__(for_block_threads) frame_of_reference_compress_by_block(
+	int_t<C>*        __restrict__  compressed,
+	int32_t*         __restrict__  segment_model_coefficients,
+	const int_t<U>*  __restrict__  uncompressed,
+	size_type<IndexSize>           length,
+	size_type<IndexSize>           segment_length,
+	unsigned*                      status)
+{
+	constexpr unsigned dim = (Model == model_linear) ? 2 : 1;
+	constexpr unsigned E = 16 / U;
+	__shared__ int64_t warp_lowest[2][for_block_threads / warp_size]; // (double-buffered by segment parity: one barrier per segment)
+	const uint64_t L = segment_length;
+	const uint64_t whole_segments = (uint64_t) length / L;
+	const unsigned num_vectors = (unsigned)(L / E);
+	const int64_t lowest = -((int64_t) 1 << (8 * C - 1)), highest = ((int64_t) 1 << (8 * C - 1)) - 1;
+	bool overflow = false;
+	unsigned parity = 0;
+	for (uint64_t s = blockIdx.x; s < whole_segments; s += gridDim.x, parity ^= 1u) {
+		const int_t<U>* __restrict__ x = uncompressed + s * L;
+		byte_pack<16> held[for_block_vectors];
+		#pragma unroll
+		for (unsigned k = 0; k < for_block_vectors; k++) {
+			const unsigned v = k * for_block_threads + threadIdx.x;
+			if (v < num_vectors) { held[k] = load_pack<16>(x + (uint64_t) v * E); }
+		}
+		int64_t first = 0, c1 = 0;
+		if (Model == model_linear) {
+			first = __ldg(x);
+			const int64_t last = __ldg(x + L - 1);
+			c1 = (int64_t) rint((double)(last - first) / (double)(L > 1 ? L - 1 : 1));
+		}
+		int64_t lowest_residual = INT64_MAX;
+		#pragma unroll
+		for (unsigned k = 0; k < for_block_vectors; k++) {
+			const unsigned v = k * for_block_threads + threadIdx.x;
+			if (v < num_vectors) {
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) {
+					const int64_t residual = (int64_t)(int_t<U>) held[k].template get<U>(j) - (first + c1 * (int64_t)(v * E + j));
+					lowest_residual = residual < lowest_residual ? residual : lowest_residual;
+				}
+			}
+		}
+		lowest_residual = warp_min(lowest_residual);
+		if (lane_index() == 0) { warp_lowest[parity][warp_index_in_block()] = lowest_residual; }
+		__syncthreads();
+		#pragma unroll
+		for (unsigned w = 0; w < for_block_threads / warp_size; w++) {
+			const int64_t other = warp_lowest[parity][w];
+			lowest_residual = other < lowest_residual ? other : lowest_residual;
+		}
+		const int64_t c0 = first + (lowest_residual - lowest);
+		if (threadIdx.x == 0) {
+			segment_model_coefficients[s * dim] = (int32_t) c0;
+			if (dim == 2) { segment_model_coefficients[s * dim + 1] = (int32_t) c1; }
+		}
+		#pragma unroll
+		for (unsigned k = 0; k < for_block_vectors; k++) {
+			const unsigned v = k * for_block_threads + threadIdx.x;
+			if (v < num_vectors) {
+				byte_pack<E * C> out;
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) {
+					const int64_t offset = (int64_t)(int_t<U>) held[k].template get<U>(j) - (c0 + c1 * (int64_t)(v * E + j));
+					if (offset < lowest || offset > highest) { overflow = true; }
+					out.template set<C>(j, (uint_t<C>)(int_t<C>) offset);
+				}
+				store_pack<E * C>(compressed + s * L + (uint64_t) v * E, out);
+			}
 		}
 	}
 	if (overflow) { raise(status, status_unrepresentable); }
@@ -856,10 +981,15 @@ __global__ void run_anchors(
 // -------------------------------------------------------------------------------------------------
 // Discard zero bytes, variable width (format: discard_zero_bytes_variable.cuh:335-439).  Element i is stored in
 // size_i = max(significant bytes of x[i], min_size) bytes; size_i - min_size goes into a `bits`-wide field.
-//   pass 1  variable_width_segment_bytes   a warp per segment: the bytes its elements take
-//   scan    exclusive_sum_by_one_block     -> byte offset of every segment = position_anchors
-//   pass 2  variable_width_emit            a warp per segment: sizes again, a running offset, the bytes
-//           variable_width_pack_sizes      a thread per size container
+//   pass 1  variable_width_sizes           a warp per segment, 16-byte vectors of elements: the bytes the segment takes and
+//                                          -- where containers straddle neither a lane's vector nor segments -- the size
+//                                          containers, each OR-ed together from the fields of neighbouring lanes
+//           variable_width_pack_sizes      (otherwise) a thread per size container
+//   scan    chunk_exclusive_sums etc.      -> byte offset of every segment = position_anchors
+//   pass 2  variable_width_emit            a warp per segment: sizes again, a warp scan per 512 bytes of elements, the bytes
+//                                          compacted into a shared-memory window laid out in the phase of the destination
+//                                          (window byte p <-> global byte base + p, base 16-byte aligned), whole 16-byte
+//                                          chunks of which are flushed with vector stores every `emit_window_steps` steps
 // -------------------------------------------------------------------------------------------------
 template <unsigned U>
 __device__ __forceinline__ unsigned significant_bytes(uint_t<U> x)
@@ -868,9 +998,41 @@ __device__ __forceinline__ unsigned significant_bytes(uint_t<U> x)
 	return x == 0 ? 0u : (unsigned)((32 - __clz((int)(uint32_t) x) + 7) / 8);
 }
 
+// a lane's 16 / U elements i ... of a segment of `count`, zeroes beyond its end
 template <unsigned U>
-__global__ void variable_width_segment_bytes(
+__device__ __forceinline__ byte_pack<16> load_segment_vector(const uint_t<U>* __restrict__ segment, uint64_t i, uint64_t count, bool aligned)
+{
+	constexpr unsigned E = 16 / U;
+	if (aligned && i + E <= count) { return load_pack<16>(segment + i); }
+	byte_pack<16> v;
+	#pragma unroll
+	for (unsigned j = 0; j < E; j++) { v.template set<U>(j, (i + j < count) ? segment[i + j] : (uint_t<U>) 0); }
+	return v;
+}
+
+constexpr unsigned sizes_steps = 4; // 16-byte loads a lane has in flight
+
+// The loads of one iteration of a segment's warp -- `Steps` steps of 32 lanes x 16 bytes from element `first` of the segment
+// on -- all issued before any is used.  Whole: every lane's vectors lie inside the segment and are 16-byte aligned.
+template <unsigned U, unsigned Steps, bool Whole>
+__device__ __forceinline__ void load_steps(byte_pack<16> (&v)[Steps], const uint_t<U>* __restrict__ segment, uint64_t first, uint64_t count, bool aligned)
+{
+	constexpr unsigned E = 16 / U;
+	#pragma unroll
+	for (unsigned k = 0; k < Steps; k++) {
+		const uint64_t i = first + (uint64_t) k * warp_size * E + lane_index() * E;
+		if (Whole) { v[k] = load_pack<16>(segment + i); }
+		else if (i < count) { v[k] = load_segment_vector<U>(segment, i, count, aligned); }
+	}
+}
+
+// packed_element_sizes: null unless the launcher has established that x is 16-byte aligned, that the segment length is a
+// multiple both of the elements in a 16-byte vector and of those in a container, and that a container holds the elements of a
+// power-of-two number of vectors
+template <unsigned U, unsigned CS>
+__global__ void variable_width_sizes(
 	uint64_t*         __restrict__  segment_bytes,
+	uint_t<CS>*       __restrict__  packed_element_sizes,
 	const uint_t<U>*  __restrict__  x,
 	uint64_t                        length,
 	uint64_t                        segment_length,
@@ -878,23 +1040,65 @@ __global__ void variable_width_segment_bytes(
 	unsigned                        bits,
 	unsigned*                       status)
 {
+	constexpr unsigned E = 16 / U;
+	constexpr unsigned span = sizes_steps * warp_size * E; // elements per iteration
+	using container_t = uint_t<CS>;
 	const uint64_t num_segments = (length + segment_length - 1) / segment_length;
-	bool unrepresentable = false;
+	const bool aligned = is_aligned_to(x, 16) && segment_length % E == 0;
+	const unsigned lane = lane_index();
+	const unsigned per_container = (8 * CS) / bits;
+	const unsigned group = per_container / E;                      // lanes whose vectors share a container (a power of two)
+	const unsigned log2_per_container = 31 - __clz((int) per_container);
+	const unsigned field_shift = (lane & (group - 1)) * E * bits;
+	const bool writes_container = (lane & (group - 1)) == 0;
+	const unsigned field_mask = (bits >= 32) ? ~0u : ((1u << bits) - 1);
+	unsigned overflow = 0; // bits of size - min_size beyond the field
 	for (uint64_t s = global_warp_index(); s < num_segments; s += num_warps_in_grid()) {
 		const uint64_t start = s * segment_length;
 		const uint64_t count = minimum<uint64_t>(segment_length, length - start);
+		const uint_t<U>* const segment = x + start;
 		uint64_t bytes = 0;
-		for (uint64_t i = lane_index(); i < count; i += warp_size) {
-			const unsigned size = max(significant_bytes<U>(x[start + i]), min_size);
-			if (bits < 32 && ((size - min_size) >> bits) != 0) { unrepresentable = true; }
-			bytes += size;
-		}
+		auto iteration = [&](uint64_t first, auto whole) {
+			constexpr bool Whole = decltype(whole)::value;
+			byte_pack<16> v[sizes_steps];
+			load_steps<U, sizes_steps, Whole>(v, segment, first, count, aligned);
+			unsigned iteration_bytes = 0;
+			#pragma unroll
+			for (unsigned k = 0; k < sizes_steps; k++) {
+				const uint64_t i = first + (uint64_t) k * warp_size * E + lane * E;
+				if (!Whole && i - lane * E >= count) { break; }
+				container_t fields = 0;
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) {
+					if (Whole || i + j < count) {
+						const unsigned size = max(significant_bytes<U>(v[k].template get<U>(j)), min_size);
+						const unsigned excess = size - min_size;
+						if (bits < 32) { overflow |= excess >> bits; }
+						iteration_bytes += size;
+						fields |= (container_t)(excess & field_mask) << (j * bits);
+					}
+				}
+				if (packed_element_sizes != nullptr) {
+					container_t container = fields << field_shift;
+					for (unsigned d = 1; d < group; d <<= 1) { container |= __shfl_xor_sync(full_mask, container, d); }
+					if (writes_container && (Whole || i < count)) { packed_element_sizes[(start + i) >> log2_per_container] = container; }
+				}
+			}
+			bytes += iteration_bytes;
+		};
+		const uint64_t whole_end = aligned ? count / span * span : 0;
+		for (uint64_t first = 0; first < whole_end; first += span) { iteration(first, ::std::true_type{}); }
+		for (uint64_t first = whole_end; first < count; first += span) { iteration(first, ::std::false_type{}); }
 		bytes = warp_inclusive_sum(bytes);
-		if (lane_index() == warp_size - 1) { segment_bytes[s] = bytes; }
+		if (lane == warp_size - 1) { segment_bytes[s] = bytes; }
 	}
-	if (unrepresentable) { raise(status, status_unrepresentable); }
+	if (overflow != 0) { raise(status, status_unrepresentable); }
 }
 
+constexpr unsigned emit_window_steps = 4;                              // steps of 32 lanes x 16 bytes of elements between flushes
+constexpr unsigned emit_window_bytes = emit_window_steps * 512 + 32;   // + the destination's phase or the carried partial chunk
+
+// dynamic shared memory: emit_window_bytes per warp of the block
 template <unsigned IndexSize, unsigned U>
 __global__ void variable_width_emit(
 	uint8_t*           __restrict__  compressed_data,
@@ -908,7 +1112,12 @@ __global__ void variable_width_emit(
 	uint64_t                         data_capacity,
 	unsigned*                        status)
 {
+	extern __shared__ __align__(16) unsigned char emit_windows[];
+	constexpr unsigned E = 16 / U;
+	constexpr unsigned span = emit_window_steps * warp_size * E; // elements per window
+	unsigned char* const window = emit_windows + warp_index_in_block() * emit_window_bytes;
 	const uint64_t num_segments = (length + segment_length - 1) / segment_length;
+	const bool aligned = is_aligned_to(x, 16) && segment_length % E == 0;
 	const unsigned lane = lane_index();
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		const uint64_t total = segment_offsets[num_segments];
@@ -919,22 +1128,75 @@ __global__ void variable_width_emit(
 	for (uint64_t s = global_warp_index(); s < num_segments; s += num_warps_in_grid()) {
 		const uint64_t start = s * segment_length;
 		const uint64_t count = minimum<uint64_t>(segment_length, length - start);
-		uint64_t offset = segment_offsets[s];
+		const uint_t<U>* const segment = x + start;
+		const uint64_t offset = segment_offsets[s];
 		if (lane == 0) {
 			if (IndexSize < 8 && (offset >> (8 * IndexSize)) != 0) { index_overflow = true; }
 			position_anchors[s] = (uint_t<IndexSize>) offset;
 		}
-		for (uint64_t base = 0; base < count; base += warp_size) {
-			const uint64_t i = base + lane;
-			const uint_t<U> value = (i < count) ? x[start + i] : (uint_t<U>) 0;
-			const unsigned size = (i < count) ? max(significant_bytes<U>(value), min_size) : 0u;
-			const unsigned inclusive = warp_inclusive_sum(size);
-			const uint64_t mine = offset + inclusive - size;
-			if (mine + size <= data_capacity) {
-				for (unsigned b = 0; b < size; b++) { compressed_data[mine + b] = (uint8_t)((uint64_t) value >> (8 * b)); }
+		// window byte p <-> compressed_data[window_offset + p], that address 16-byte aligned at p = 0; the segment's first byte
+		// is window byte `phase`, the bytes before it belong to the previous segment (another warp's)
+		const unsigned phase = (unsigned)((reinterpret_cast<uintptr_t>(compressed_data) + offset) & 15u);
+		int64_t window_offset = (int64_t) offset - (int64_t) phase;
+		unsigned fill = phase;
+		bool foreign_head = phase != 0;
+		auto fill_window = [&](uint64_t first, auto whole) {
+			constexpr bool Whole = decltype(whole)::value;
+			byte_pack<16> v[emit_window_steps];
+			load_steps<U, emit_window_steps, Whole>(v, segment, first, count, aligned);
+			#pragma unroll
+			for (unsigned k = 0; k < emit_window_steps; k++) {
+				const uint64_t i = first + (uint64_t) k * warp_size * E + lane * E;
+				if (!Whole && i - lane * E >= count) { break; }
+				unsigned size[E], total = 0;
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) {
+					size[j] = (Whole || i + j < count) ? max(significant_bytes<U>(v[k].template get<U>(j)), min_size) : 0u;
+					total += size[j];
+				}
+				const unsigned inclusive = warp_inclusive_sum(total);
+				unsigned at = fill + inclusive - total;
+				#pragma unroll
+				for (unsigned j = 0; j < E; j++) {
+					const uint_t<U> value = v[k].template get<U>(j);
+					#pragma unroll
+					for (unsigned b = 0; b < U; b++) { if (b < size[j]) { window[at + b] = (unsigned char)(value >> (8 * b)); } }
+					at += size[j];
+				}
+				fill += __shfl_sync(full_mask, inclusive, warp_size - 1);
 			}
-			offset += __shfl_sync(full_mask, inclusive, warp_size - 1);
+		};
+		const uint64_t whole_end = aligned ? count / span * span : 0;
+		for (uint64_t first = 0; first < count; first += span) {
+			if (first < whole_end) { fill_window(first, ::std::true_type{}); } else { fill_window(first, ::std::false_type{}); }
+			__syncwarp();
+			// flush the whole 16-byte chunks; the partial one at the end is carried to the front of the window
+			const unsigned whole_chunks = fill / 16;
+			for (unsigned c = lane; c < whole_chunks; c += warp_size) {
+				const int64_t position = window_offset + 16 * (int64_t) c;
+				const unsigned begin = (c == 0 && foreign_head) ? phase : 0u;
+				if (begin == 0 && (uint64_t) position + 16 <= data_capacity) {
+					store_streaming_16(compressed_data + position, *reinterpret_cast<const uint4*>(window + 16 * c));
+				}
+				else {
+					for (unsigned b = begin; b < 16; b++) { if ((uint64_t)(position + b) < data_capacity) { compressed_data[position + b] = window[16 * c + b]; } }
+				}
+			}
+			const unsigned remaining = fill - 16 * whole_chunks;
+			const unsigned char carried = (whole_chunks > 0 && lane < remaining) ? window[16 * whole_chunks + lane] : (unsigned char) 0;
+			__syncwarp();
+			if (whole_chunks > 0) {
+				if (lane < remaining) { window[lane] = carried; }
+				window_offset += 16 * (int64_t) whole_chunks;
+				fill = remaining;
+				foreign_head = false;
+			}
+			__syncwarp();
 		}
+		for (unsigned b = lane; b < fill; b += warp_size) {
+			if (!(foreign_head && b < phase) && (uint64_t)(window_offset + b) < data_capacity) { compressed_data[window_offset + b] = window[b]; }
+		}
+		__syncwarp();
 	}
 	if (index_overflow) { raise(status, status_index_overflow); }
 }

@@ -119,7 +119,8 @@ def test_dictionary(library, I, U, DI, D):
 @pytest.mark.gpu
 @pytest.mark.parametrize("I,U,C,model", [(4, 2, 1, "linear"), (4, 4, 1, "linear"), (4, 4, 2, "linear"), (8, 4, 2, "linear"),
                                          (4, 2, 1, "constant"), (4, 4, 1, "constant"), (4, 4, 2, "constant")])
-@pytest.mark.parametrize("n,L", [(64 * 1024, 1024), (50000 + 13, 1020), (7, 4096)])
+@pytest.mark.parametrize("n,L", [(64 * 1024, 1024), (50000 + 13, 1020), (7, 4096),
+                                 (200000 + 5, 4096), (4 * 8192, 8192)])  # segments a CTA holds in registers (+ a ragged last one)
 def test_frame_of_reference(library, I, U, C, model, n, L):
     r = cases.rng(34, U, C, n, L)
     # a column which a segment-wise model fits: a level (and, for the linear model, a slope) per segment plus noise within the
