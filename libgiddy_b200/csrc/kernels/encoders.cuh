@@ -775,7 +775,14 @@ __device__ __forceinline__ void load_16_elements(uint_t<U> (&v)[run_tile_per_thr
 {
 	static_assert(run_tile_per_thread == 16, "a thread's elements are loaded as 16 x U bytes");
 	if (vector_loads && first + run_tile_per_thread <= limit) {
-		const byte_pack<16 * U> pack = load_pack<16 * U>(x + first);
+		// (through L1: a thread's 16-byte pieces are consecutive, so two of them share a 32-byte sector -- and a warp's load
+		// instruction touches every other piece of the sectors it fetches -- which a no-allocate load would fetch twice)
+		byte_pack<16 * U> pack;
+		#pragma unroll
+		for (unsigned k = 0; k < U; k++) {
+			const uint4 t = __ldg(reinterpret_cast<const uint4*>(x + first) + k);
+			pack.u32[4 * k] = t.x; pack.u32[4 * k + 1] = t.y; pack.u32[4 * k + 2] = t.z; pack.u32[4 * k + 3] = t.w;
+		}
 		#pragma unroll
 		for (unsigned j = 0; j < run_tile_per_thread; j++) { v[j] = pack.template get<U>(j); }
 	}
