@@ -8,6 +8,7 @@
 
     make sass && python scripts/sass_summary.py r01
 """
+import io
 import os
 import re
 import subprocess
@@ -61,7 +62,8 @@ def main():
             if any(name.replace("u>", ">").replace("u,", ",") == h for h in HEADLINE):
                 safe = re.sub(r"[^A-Za-z0-9]+", "_", name).strip("_")
                 import gzip
-                with gzip.open(os.path.join(out_dir, safe + ".sass.gz"), "wt") as f:  # (gzip'ed: listings are evidence, not reading matter)
+                with open(os.path.join(out_dir, safe + ".sass.gz"), "wb") as raw, gzip.GzipFile(fileobj=raw, mode="wb", mtime=0) as binary, \
+                        io.TextIOWrapper(binary) as f:  # (gzip'ed, reproducibly: listings are evidence, not reading matter)
                     f.write("Function : %s\n(%s; nvcc 12.9 -O3 -gencode arch=compute_100a,code=sm_100a)\n%s" % (name, mangled, body))
     rows.sort()
     with open(os.path.join(ROOT, "profiles", "sass_%s_summary.md" % tag), "w") as f:
