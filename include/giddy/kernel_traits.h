@@ -70,6 +70,9 @@
 #ifndef GIDDY_PATCHED_UNROLL
 #define GIDDY_PATCHED_UNROLL 2
 #endif
+#ifndef GIDDY_PATCHED_INDEX_BLOCK_THREADS
+#define GIDDY_PATCHED_INDEX_BLOCK_THREADS 64       /* expand_and_index_compressed_indices: a CTA per anchoring period */
+#endif
 #ifndef GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR
 #define GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR 4
 #endif

@@ -116,7 +116,7 @@ giddy_status_t for_launch(void* stream, const giddy_launch_config_t* cfg, void* 
 		// periods whose decoded positions fit 32 KiB keep them in shared memory and build the tile index in the same kernel
 		// (one launch and one pass over the positions less); longer ones leave it to patch_tile_ranges
 		if (fused_index) {
-			kernels::patched_detail::expand_and_index_compressed_indices<I, II, II><<<(unsigned) (periods < 0x7fffffffull ? periods : 0x7fffffffull), 128,
+			kernels::patched_detail::expand_and_index_compressed_indices<I, II, II><<<(unsigned) (periods < 0x7fffffffull ? periods : 0x7fffffffull), GIDDY_PATCHED_INDEX_BLOCK_THREADS,
 				(unsigned)(anchoring_period * I), s>>>(
 				static_cast<uint_t<I>*>(positions), static_cast<kernels::patched_detail::patch_range_t<I>*>(workspace),
 				static_cast<const uint_t<II>*>(run_lengths), static_cast<const unsigned char*>(offset_sizes),
