@@ -179,7 +179,10 @@ struct traits {
 	static const void* kernel() { return giddy_b200_dictionary_compress_kernel(IndexSize, UncompressedSize, DictionaryIndexSize); }
 	static void configure(detail::described_params_t& p, const kernel_t::arguments_type& a)
 	{
-		detail::configure_streaming(p, detail::required<::std::size_t>(a, "data_length"), (16 / UncompressedSize) * GIDDY_ELEMENTWISE_UNROLL);
+		// every block builds its own copy of the dictionary (a hash table, or the entries for a binary search) in shared memory:
+		// a few blocks per multiprocessor which stride over the column, not a block per tile
+		const ::std::size_t per_tile = (::std::size_t) GIDDY_ELEMENTWISE_BLOCK_THREADS * (16 / UncompressedSize) * GIDDY_ELEMENTWISE_UNROLL;
+		detail::configure_tiled(p, (detail::required<::std::size_t>(a, "data_length") + per_tile - 1) / per_tile, GIDDY_ELEMENTWISE_BLOCK_THREADS);
 		// the dictionary is searched in shared memory when it fits what a block gets without asking
 		const ::std::size_t bytes = detail::required<::std::size_t>(a, "num_dictionary_entries") * UncompressedSize;
 		if (bytes <= 32 * 1024) { p.dynamic_shared_memory_requirement.per_block = (shared_memory_size_t) bytes; }

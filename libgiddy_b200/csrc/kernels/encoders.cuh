@@ -814,38 +814,36 @@ __global__ void __launch_bounds__(run_tile_threads) run_tile_summaries_fast(
 	const uint_t<U>*     __restrict__  x,
 	uint64_t                           length)
 {
-	__shared__ uint64_t shared_first[run_tile_threads / warp_size], shared_last[run_tile_threads / warp_size];
-	__shared__ unsigned shared_count[run_tile_threads / warp_size];
+	__shared__ unsigned shared_first[2][run_tile_threads / warp_size], shared_last[2][run_tile_threads / warp_size], shared_count[2][run_tile_threads / warp_size];
 	const bool vector_loads = is_aligned_to(x, 16);
 	const uint64_t num_tiles = (length + run_tile_elements - 1) / run_tile_elements;
-	for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+	unsigned iteration = 0;
+	for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, iteration++) {
 		const uint64_t tile_start = tile * run_tile_elements;
 		const uint64_t first = tile_start + (uint64_t) threadIdx.x * run_tile_per_thread;
 		uint_t<U> v[run_tile_per_thread];
 		load_16_elements<U>(v, x, first, length, vector_loads);
 		const unsigned mask = natural_heads_of_16<U>(v, x, first, length);
-		// warp: first head (min), last head + 1 (max), head count (sum)
-		uint64_t lowest = mask ? first + (__ffs(mask) - 1) : no_position;
-		uint64_t highest = mask ? first + (32 - __clz(mask)) : 0; // position + 1
+		// warp: first head (min), last head + 1 (max), head count (sum) -- tile-relative, 32-bit: one REDUX each
+		const unsigned thread_first = threadIdx.x * run_tile_per_thread;
+		unsigned lowest = mask ? thread_first + (__ffs(mask) - 1) : ~0u;
+		unsigned highest = mask ? thread_first + (32 - __clz(mask)) : 0u; // position + 1
 		unsigned count = __popc(mask);
-		#pragma unroll
-		for (unsigned d = 16; d > 0; d >>= 1) {
-			const uint64_t l = __shfl_xor_sync(full_mask, (unsigned long long) lowest, d);
-			const uint64_t h = __shfl_xor_sync(full_mask, (unsigned long long) highest, d);
-			lowest = l < lowest ? l : lowest; highest = h > highest ? h : highest;
-			count += __shfl_xor_sync(full_mask, count, d);
-		}
-		if (lane_index() == 0) { shared_first[warp_index_in_block()] = lowest; shared_last[warp_index_in_block()] = highest; shared_count[warp_index_in_block()] = count; }
+		lowest = __reduce_min_sync(full_mask, lowest);
+		highest = __reduce_max_sync(full_mask, highest);
+		count = __reduce_add_sync(full_mask, count);
+		const unsigned parity = iteration & 1u; // (double-buffered: one barrier per tile)
+		if (lane_index() == 0) { shared_first[parity][warp_index_in_block()] = lowest; shared_last[parity][warp_index_in_block()] = highest; shared_count[parity][warp_index_in_block()] = count; }
 		__syncthreads();
-		if (threadIdx.x == 0) {
-			for (unsigned w = 1; w < run_tile_threads / warp_size; w++) {
-				lowest = shared_first[w] < lowest ? shared_first[w] : lowest;
-				highest = shared_last[w] > highest ? shared_last[w] : highest;
-				count += shared_count[w];
+		if (threadIdx.x < warp_size) {
+			const bool has = threadIdx.x < run_tile_threads / warp_size;
+			lowest = __reduce_min_sync(full_mask, has ? shared_first[parity][threadIdx.x] : ~0u);
+			highest = __reduce_max_sync(full_mask, has ? shared_last[parity][threadIdx.x] : 0u);
+			count = __reduce_add_sync(full_mask, has ? shared_count[parity][threadIdx.x] : 0u);
+			if (threadIdx.x == 0) {
+				summaries[tile] = { lowest == ~0u ? no_position : tile_start + lowest, highest == 0 ? no_position : tile_start + highest - 1, count };
 			}
-			summaries[tile] = { lowest, highest == 0 ? no_position : highest - 1, count };
 		}
-		__syncthreads();
 	}
 }
 
@@ -887,14 +885,13 @@ __global__ void __launch_bounds__(run_tile_threads) run_emit_fast(
 		const unsigned inclusive = warp_inclusive_sum(count);
 		if (lane_index() == warp_size - 1) { warp_totals[warp_index_in_block()] = inclusive; }
 		__syncthreads();
-		if (threadIdx.x == 0) {
-			unsigned running = 0;
-			for (unsigned w = 0; w < run_tile_threads / warp_size; w++) { const unsigned t = warp_totals[w]; warp_totals[w] = running; running += t; }
-			warp_totals[run_tile_threads / warp_size] = running;
+		unsigned slot = inclusive - count, tile_heads = 0;
+		#pragma unroll
+		for (unsigned w = 0; w < run_tile_threads / warp_size; w++) { // (every thread sums the warps' totals itself: no second barrier)
+			const unsigned t = warp_totals[w];
+			if (w < warp_index_in_block()) { slot += t; }
+			tile_heads += t;
 		}
-		__syncthreads();
-		unsigned slot = warp_totals[warp_index_in_block()] + inclusive - count;
-		const unsigned tile_heads = warp_totals[run_tile_threads / warp_size];
 		#pragma unroll
 		for (unsigned j = 0; j < run_tile_per_thread; j++) { // (statically indexed: the elements stay in registers)
 			if ((mask >> j) & 1u) {
