@@ -324,13 +324,16 @@ __device__ __forceinline__ void decode_segment_staged(
 		// the body of the byte range goes through TMA, its < 16 trailing bytes through four lanes
 		auto stage_bytes = [&](uint64_t past_last_byte) {
 			const uintptr_t first = reinterpret_cast<uintptr_t>(compressed_data) + tile_first_byte;
-			// (a next anchor is a hint: whatever lies between it and the tile's last byte -- padding between segments, or
-			// a corrupt anchor -- is never decoded, so never staged either: a tile's elements occupy at most tile x U bytes)
-			const uintptr_t past_last = minimum<uintptr_t>(reinterpret_cast<uintptr_t>(compressed_data) + past_last_byte,
-				first + (uintptr_t) tile_elements * U);
+			const uintptr_t past_last = reinterpret_cast<uintptr_t>(compressed_data) + past_last_byte;
 			const uintptr_t body_first = first & ~(uintptr_t) 15;
 			const uintptr_t body_past_last = (past_last & ~(uintptr_t) 15) > body_first ? (past_last & ~(uintptr_t) 15) : body_first;
-			const uint32_t body_bytes = (uint32_t)(body_past_last - body_first);
+			// (a next anchor is a hint: whatever lies between it and the tile's last byte -- padding between segments, or a
+			// corrupt anchor -- is never decoded, so never staged either: a tile's elements end within tile x U bytes of the
+			// first one.  Two 32-bit guards on what goes into shared memory; clamping the 64-bit address instead, ahead of the
+			// copy's issue, costs the kernel 3 %.)
+			constexpr uint32_t most_body_bytes = tile_elements * U + 32;
+			static_assert(most_body_bytes % 16 == 0 && most_body_bytes + 32 <= tile_storage<U>::data_bytes, "the clamped copy and its trailing words fit the data area");
+			const uint32_t body_bytes = minimum<uint32_t>((uint32_t)(body_past_last - body_first), most_body_bytes);
 			if (lane == 0) {
 				fence_proxy_async_shared();
 				if (body_bytes > 0) {
@@ -343,7 +346,7 @@ __device__ __forceinline__ void decode_segment_staged(
 			// from the word holding the first byte
 			const uintptr_t tail_first = (body_bytes > 0) ? body_past_last : (first & ~(uintptr_t) 3);
 			const uintptr_t tail_word = tail_first + 4 * lane;
-			if (lane < 8 && tail_word < past_last) {
+			if (lane < 8 && tail_word < past_last && (uint64_t)(tail_word - body_first) < most_body_bytes + 32 - 3) {
 				*reinterpret_cast<uint32_t*>(tile.data + (tail_word - body_first)) = __ldg(reinterpret_cast<const uint32_t*>(tail_word));
 			}
 		};
