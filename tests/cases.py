@@ -224,7 +224,7 @@ def dzbf_case(seed, n, U, C, I=4):
     return Case("dzbf-I%d-U%d-C%d-n%d" % (I, U, C, n), "discard_zero_bytes_fixed", {"compressed_input": compressed}, dict(n=n), expected, launch)
 
 
-def dzbv_case(seed, n, L, U, CS, bits, min_size, I=4, ref_ok=None):
+def dzbv_case(seed, n, L, U, CS, bits, min_size, I=4, ref_ok=None, gap=0):
     r = rng(8, seed, n, L, U, CS, bits)
     max_size = min(U, min_size + (1 << bits) - 1)
     widths = r.integers(min_size, max_size + 1, n)
@@ -235,6 +235,14 @@ def dzbv_case(seed, n, L, U, CS, bits, min_size, I=4, ref_ok=None):
         column[mask] = raw[mask] >> UINT[U](8 * (U - w)) if w < U else raw[mask]
     enc = E.discard_zero_bytes_variable_encode(column, L, CS, bits, min_size, I)
     sizes = enc.pop("element_sizes")
+    if gap:  # `gap` bytes of padding after every segment: a segment's bytes end before the next one's anchor
+        anchors = enc["position_anchors"].astype(np.uint64)
+        ends = np.concatenate((anchors[1:], [len(enc["compressed_data"])])).astype(np.uint64)
+        pieces = []
+        for a, b in zip(anchors, ends):
+            pieces += [enc["compressed_data"][int(a):int(b)], np.full(gap, 0xEE, np.uint8)]
+        enc["compressed_data"] = np.concatenate(pieces)
+        enc["position_anchors"] = (anchors + np.arange(len(anchors), dtype=np.uint64) * np.uint64(gap)).astype(enc["position_anchors"].dtype)
     # the kernels may read the aligned word holding the stream's last byte: keep the buffer word-padded
     enc["compressed_data"] = np.concatenate((enc["compressed_data"], np.zeros(8, np.uint8)))
     expected = O.discard_zero_bytes_variable(enc["compressed_data"], enc["packed_element_sizes"], enc["position_anchors"], L, n, min_size, bits, U)
@@ -243,8 +251,8 @@ def dzbv_case(seed, n, L, U, CS, bits, min_size, I=4, ref_ok=None):
     def launch(out, t, library, limits):
         S.discard_zero_bytes_variable(out, t["compressed_data"], t["packed_element_sizes"], t["position_anchors"], L, n, min_size, bits,
                                       uncompressed_size=U, container_size=CS, index_size=I, library=library, limits=limits)
-    return Case("dzbv-I%d-U%d-CS%d-b%d-m%d-n%d-L%d" % (I, U, CS, bits, min_size, n, L), "discard_zero_bytes_variable", enc, dict(n=n, L=L),
-                expected, launch, ref_ok=(n % L == 0) if ref_ok is None else ref_ok)
+    return Case("dzbv-I%d-U%d-CS%d-b%d-m%d-n%d-L%d%s" % (I, U, CS, bits, min_size, n, L, "-gap%d" % gap if gap else ""), "discard_zero_bytes_variable", enc,
+                dict(n=n, L=L), expected, launch, ref_ok=((n % L == 0) if ref_ok is None else ref_ok) and not gap)
 
 
 def dzbv_delta_case(seed, n, L, U, C, CS, bits, min_size, I=4):
@@ -494,6 +502,10 @@ def all_cases():
     cases.append(dzbv_case(12, 33000, 1024, 4, 4, 4, 0, ref_ok=False))
     cases.append(dzbv_case(13, 64 * 1024, 1024, 8, 4, 2, 5, ref_ok=False))
     cases.append(dzbv_case(14, 20, 1024, 4, 4, 2, 1, ref_ok=False))
+    # padding between segments: what lies between a segment's last byte and the next anchor is never decoded (nor staged)
+    cases.append(dzbv_case(15, 40 * 1024, 1024, 4, 4, 2, 1, gap=8))
+    cases.append(dzbv_case(16, 20 * 1024 + 3, 1024, 4, 4, 2, 1, gap=5000))           # farther than a whole tile of bytes
+    cases.append(dzbv_case(17, 16 * 1024, 2048, 8, 4, 2, 5, gap=13))                 # two tiles per segment, unaligned segments
     # Extension: Delta of DZB-variable, fused (5 keys)
     for (I, U, C, CS) in [(4, 8, 4, 4), (4, 8, 4, 8), (4, 8, 2, 4), (4, 4, 2, 4), (8, 8, 4, 4)]:
         bits = 2 if C == 4 else 1
