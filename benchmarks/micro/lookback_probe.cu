@@ -12,7 +12,7 @@
 #define CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s failed: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
 
 template <unsigned U, unsigned C>
-void run(size_t n, int blocks_per_sm, bool static_tiles, const char* label)
+void run(size_t n, int blocks_per_sm, int static_tiles, const char* label)
 {
 	using namespace giddy;
 	std::vector<uint_t<C>> deltas(n);
@@ -38,7 +38,10 @@ void run(size_t n, int blocks_per_sm, bool static_tiles, const char* label)
 			const size_t staging = GIDDY_DELTA_LOOK_BACK_SHARED_BYTES(U, C, threads);
 			const void* kernel = reinterpret_cast<const void*>(kernels::delta_decompress_long_segments_staged<4, U, C>);
 			CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) staging));
-			CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(threads), arguments, staging, 0));
+			if (static_tiles == 2) { // a plain launch of the same grid (all of it resident here): what the cooperative launch itself costs
+				kernels::delta_decompress_long_segments_staged<4, U, C><<<grid, threads, staging>>>(out, in, anchor, n32, n32, workspace);
+			}
+			else { CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(threads), arguments, staging, 0)); }
 		}
 		else { kernels::delta_decompress_long_segments<4, U, C><<<grid, threads>>>(out, in, anchor, n32, n32, workspace); }
 	};
@@ -97,7 +100,7 @@ int main(int argc, char** argv)
 {
 	const char* label = argc > 1 ? argv[1] : "";
 	const int blocks_per_sm = argc > 2 ? atoi(argv[2]) : GIDDY_DELTA_LOOK_BACK_BLOCKS_PER_MULTIPROCESSOR;
-	const bool static_tiles = argc > 3 ? atoi(argv[3]) != 0 : true;
+	const int static_tiles = argc > 3 ? atoi(argv[3]) : 1;
 	run<8, 4>((size_t) 1 << 26, blocks_per_sm, static_tiles, label);
 	run<4, 1>((size_t) 1 << 27, blocks_per_sm, static_tiles, label);
 	return 0;

@@ -870,13 +870,18 @@ __global__ void __launch_bounds__(run_tile_threads) run_emit_fast(
 		const uint64_t first = tile_start + (uint64_t) threadIdx.x * run_tile_per_thread;
 		uint_t<U> v[run_tile_per_thread];
 		load_16_elements<U>(v, x, first, length, vector_loads);
+		// (the tile's metadata are requested along with its elements: one round trip to memory per tile, not three)
+		const uint64_t base = __ldg(placement + tile);
+		const bool may_split = max_run_length != 0 && tile != 0;
+		const uint64_t origin = may_split ? __ldg(open_run_start + tile) : 0;
+		const uint64_t first_head = may_split ? __ldg(&summaries[tile].first_head) : no_position;
 		unsigned mask = natural_heads_of_16<U>(v, x, first, length);
 		// the one split point this tile can hold: in the part of the open run which precedes the tile's first natural head
-		if (max_run_length != 0 && tile != 0) {
-			const uint64_t origin = open_run_start[tile];
-			const uint64_t steps = (tile_start - origin + max_run_length - 1) / max_run_length; // smallest k with origin + k * M >= tile_start
-			const uint64_t split = origin + (steps == 0 ? max_run_length : steps * max_run_length);
-			const uint64_t first_head = summaries[tile].first_head;
+		if (may_split) {
+			// the first split point of the open run at or after the tile's start: origin + k * M for the smallest k >= 1 which gets
+			// there (runs shorter than M, the usual case, need no 64-bit division -- a hundred instructions per thread and tile)
+			const uint64_t distance = tile_start - origin;
+			const uint64_t split = origin + (distance <= max_run_length ? max_run_length : (distance + max_run_length - 1) / max_run_length * max_run_length);
 			const uint64_t prefix_end = (first_head == no_position) ? minimum<uint64_t>(tile_start + run_tile_elements, length) : first_head;
 			if (split < prefix_end && split >= first && split < first + run_tile_per_thread) { mask |= 1u << (unsigned)(split - first); }
 		}
@@ -892,16 +897,14 @@ __global__ void __launch_bounds__(run_tile_threads) run_emit_fast(
 			if (w < warp_index_in_block()) { slot += t; }
 			tile_heads += t;
 		}
-		#pragma unroll
-		for (unsigned j = 0; j < run_tile_per_thread; j++) { // (statically indexed: the elements stay in registers)
-			if ((mask >> j) & 1u) {
-				staged_values[slot] = v[j];
-				staged_positions[slot] = (uint16_t)(threadIdx.x * run_tile_per_thread + j);
-				slot++;
-			}
+		// (heads are sparse -- one in `mean run length` elements -- so the loop is over the mask's set bits, and a head's value is
+		// read again, out of L1, rather than selected from 16 registers)
+		for (unsigned heads = mask; heads != 0; heads &= heads - 1, slot++) {
+			const unsigned j = __ffs((int) heads) - 1;
+			staged_values[slot] = __ldg(x + first + j);
+			staged_positions[slot] = (uint16_t)(threadIdx.x * run_tile_per_thread + j);
 		}
 		__syncthreads();
-		const uint64_t base = placement[tile];
 		for (unsigned e = threadIdx.x; e < tile_heads; e += run_tile_threads) {
 			if (base + e < run_capacity) { run_data[base + e] = staged_values[e]; starts[base + e] = (Start)(tile_start + staged_positions[e]); }
 			else { raise(status, status_capacity); }
