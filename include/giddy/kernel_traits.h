@@ -64,6 +64,11 @@
 	((segment_length) >= 2 * GIDDY_DELTA_TILE_ELEMENTS(U, GIDDY_DELTA_LOOK_BACK_BLOCK_THREADS) && \
 	 ((length) + (segment_length) - 1) / (segment_length) < 8192)
 
+/* Compressors: RLE / RPE whose runs may be at least a tile long in one pass with decoupled look-back (0: two passes around scans) */
+#ifndef GIDDY_RUN_ENCODERS_SINGLE_PASS
+#define GIDDY_RUN_ENCODERS_SINGLE_PASS 1
+#endif
+
 /* Patched decoders (decode + patches in one pass): warp tiles of 32 x this many output vectors go grid-stride to the
  * warps of this many CTAs (of GIDDY_ELEMENTWISE_BLOCK_THREADS threads) per multiprocessor; an index of one patch range per
  * tile is built into a workspace before the decode. */

@@ -161,6 +161,17 @@ giddy_status_t run_common(cudaStream_t s, const giddy_launch_config_t* cfg, cons
 	auto x = static_cast<const uint_t<U>*>(in);
 	// runs limited to at least a tile's length (or not at all) have at most one split point per tile: the mask-based kernels
 	const bool fast = max_run_length == 0 || max_run_length >= enc::run_tile_elements;
+	if (fast && GIDDY_RUN_ENCODERS_SINGLE_PASS) {
+		// ONE pass over the column: a tile's first run index and open run come from its predecessors' descriptors (decoupled
+		// look-back), which live where the two-pass path keeps its summaries and placement: 32 bytes per tile, then the run
+		// count (where the later kernels look for it: placement[num_tiles]) and the ticket counter, all zeroed
+		cudaError_t error = cudaMemsetAsync(plan.summaries, 0, plan.num_tiles * 32 + 16, s);
+		if (error != cudaSuccess) { return fail_cuda(error, "cudaMemsetAsync (run encoder tile descriptors)"); }
+		const unsigned enough = helper_blocks(plan.num_tiles, 1) / 2; // 8 CTAs per multiprocessor
+		enc::run_encode_single_pass<U, uint64_t><<<blocks < enough ? blocks : enough, enc::run_tile_threads, 0, s>>>(static_cast<uint_t<U>*>(run_data), plan.starts, x,
+			plan.summaries, n, max_run_length, run_capacity, status);
+		return launched("kernel launch (run encoding, one pass)");
+	}
 	if (fast) { enc::run_tile_summaries_fast<U><<<blocks, enc::run_tile_threads, 0, s>>>(plan.summaries, x, n); }
 	else { enc::run_tile_summaries<U><<<blocks, enc::run_tile_threads, 0, s>>>(plan.summaries, x, n, max_run_length); }
 	giddy_status_t result = launched("kernel launch (run tile summaries)");

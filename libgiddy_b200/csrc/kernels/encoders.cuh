@@ -17,6 +17,7 @@
 #define GIDDY_B200_KERNELS_ENCODERS_CUH_
 
 #include "common.cuh"
+#include "delta.cuh" // the tile descriptors of the decoupled look-back
 
 namespace giddy {
 namespace kernels {
@@ -910,6 +911,145 @@ __global__ void __launch_bounds__(run_tile_threads) run_emit_fast(
 			else { raise(status, status_capacity); }
 		}
 		__syncthreads();
+	}
+}
+
+// ---- the fast path in ONE pass over the column: tiles with two chained decoupled look-backs ------------------------------------
+// What the two passes compute around their scans, a tile's CTA obtains from its predecessors' descriptors (kernels/delta.cuh:
+// self-validating 16-byte descriptors, relaxed stores and loads, no fences):
+//   A  the position of the last run head at or before the tile's end -- "inclusive" at once for a tile which holds a head
+//      (nearly all do), so the run open at a tile's start is one look at the previous tile's descriptor;
+//   B  the number of run heads (natural ones + the at most one split point, known once A's look-back is) -- an ordinary
+//      sum look-back gives the index of the tile's first run.
+// Tiles are drawn from a ticket counter, in order: a tile's predecessors are running or done whatever the grid.
+// workspace: descriptors A [num_tiles], descriptors B [num_tiles], the run count (8 bytes), the ticket counter (8 bytes), zeroed.
+__device__ __forceinline__ uint64_t look_back_to_nearest(const delta_detail::tile_descriptor_t* descriptors, uint64_t tile)
+{
+	// called by one whole warp for tile >= 1: the value of the nearest predecessor whose descriptor is inclusive, all nearer
+	// ones having been seen to hold none (tile 0 is always inclusive: position 0 begins a run)
+	const unsigned lane = lane_index();
+	for (uint64_t looked = 0; ; looked += warp_size) {
+		const bool valid = looked + lane < tile;
+		uint64_t value = 0;
+		uint32_t status = delta_detail::tile_unknown;
+		while (true) {
+			if (valid && status == delta_detail::tile_unknown) { status = delta_detail::peek<8>(descriptors + (tile - 1 - (looked + lane)), value); }
+			const unsigned unseen = __ballot_sync(full_mask, valid && status == delta_detail::tile_unknown);
+			const unsigned inclusive = __ballot_sync(full_mask, valid && status == delta_detail::tile_has_inclusive);
+			const unsigned seen_prefix = unseen ? ((1u << (__ffs((int) unseen) - 1)) - 1u) : full_mask; // lanes before the first unseen one
+			const unsigned usable = inclusive & seen_prefix;
+			if (usable) { return shuffle_from(value, (unsigned) __ffs((int) usable) - 1); }
+			if (!unseen) { break; } // none of these 32 holds a head: farther back
+		}
+	}
+}
+
+template <unsigned U, typename Start>
+__global__ void __launch_bounds__(run_tile_threads) run_encode_single_pass(
+	uint_t<U>*        __restrict__  run_data,
+	Start*            __restrict__  starts,
+	const uint_t<U>*  __restrict__  x,
+	void*                           workspace,
+	uint64_t                        length,
+	uint64_t                        max_run_length,   // 0, or at least run_tile_elements
+	uint64_t                        run_capacity,
+	unsigned*                       status)
+{
+	using delta_detail::tile_descriptor_t;
+	constexpr unsigned warps = run_tile_threads / warp_size;
+	__shared__ unsigned   shared_first[warps], shared_last[warps], shared_count[warps];
+	__shared__ unsigned   warp_totals[warps];
+	__shared__ uint64_t   shared_ticket, shared_base, shared_split;
+	__shared__ uint_t<U>  staged_values[run_tile_elements];
+	__shared__ uint16_t   staged_positions[run_tile_elements];
+	const uint64_t num_tiles = (length + run_tile_elements - 1) / run_tile_elements;
+	tile_descriptor_t* const last_heads = static_cast<tile_descriptor_t*>(workspace);   // A
+	tile_descriptor_t* const head_counts = last_heads + num_tiles;                       // B
+	uint64_t* const total_out = reinterpret_cast<uint64_t*>(head_counts + num_tiles);
+	unsigned long long* const ticket_counter = reinterpret_cast<unsigned long long*>(total_out + 1);
+	const bool vector_loads = is_aligned_to(x, 16);
+	const unsigned lane = lane_index(), warp = warp_index_in_block();
+	while (true) {
+		if (threadIdx.x == 0) { shared_ticket = atomicAdd(ticket_counter, 1ull); }
+		__syncthreads();
+		const uint64_t tile = shared_ticket;
+		if (tile >= num_tiles) { return; }
+		const uint64_t tile_start = tile * run_tile_elements;
+		const uint64_t first = tile_start + (uint64_t) threadIdx.x * run_tile_per_thread;
+		uint_t<U> v[run_tile_per_thread];
+		load_16_elements<U>(v, x, first, length, vector_loads);
+		unsigned mask = natural_heads_of_16<U>(v, x, first, length);
+		// the tile's natural heads: how many, the first and the last (tile-relative; one REDUX each)
+		{
+			const unsigned thread_first = threadIdx.x * run_tile_per_thread;
+			const unsigned lowest = __reduce_min_sync(full_mask, mask ? thread_first + (__ffs((int) mask) - 1) : ~0u);
+			const unsigned highest = __reduce_max_sync(full_mask, mask ? thread_first + (32 - __clz((int) mask)) : 0u); // position + 1
+			const unsigned count = __reduce_add_sync(full_mask, (unsigned) __popc(mask));
+			if (lane == 0) { shared_first[warp] = lowest; shared_last[warp] = highest; shared_count[warp] = count; }
+		}
+		__syncthreads();
+		if (warp == 0) {
+			const bool has = lane < warps;
+			const unsigned lowest = __reduce_min_sync(full_mask, has ? shared_first[lane] : ~0u);
+			const unsigned highest = __reduce_max_sync(full_mask, has ? shared_last[lane] : 0u);
+			const unsigned natural = __reduce_add_sync(full_mask, has ? shared_count[lane] : 0u);
+			const bool has_head = highest != 0;
+			// A: a tile with a head knows its last head at once
+			if (lane == 0) {
+				if (has_head) { delta_detail::publish<8>(last_heads + tile, delta_detail::tile_has_inclusive, tile_start + highest - 1); }
+				else { delta_detail::publish<8>(last_heads + tile, delta_detail::tile_has_aggregate, 0ull); }
+			}
+			uint64_t split = no_position;
+			if (tile != 0 && (max_run_length != 0 || !has_head)) {
+				const uint64_t origin = look_back_to_nearest(last_heads, tile); // where the run open at the tile's start began
+				if (!has_head && lane == 0) { delta_detail::publish<8>(last_heads + tile, delta_detail::tile_has_inclusive, origin); }
+				if (max_run_length != 0) {
+					// the one split point this tile can hold: in the part of the open run which precedes the tile's first natural head
+					const uint64_t distance = tile_start - origin;
+					const uint64_t candidate = origin + (distance <= max_run_length ? max_run_length : (distance + max_run_length - 1) / max_run_length * max_run_length);
+					const uint64_t prefix_end = has_head ? tile_start + lowest : minimum<uint64_t>(tile_start + run_tile_elements, length);
+					if (candidate < prefix_end) { split = candidate; }
+				}
+			}
+			// B: the tile's head count, then the index of its first run
+			const uint64_t tile_heads = (uint64_t) natural + (split != no_position ? 1u : 0u);
+			uint64_t base = 0;
+			if (tile != 0) {
+				if (lane == 0) { delta_detail::publish<8>(head_counts + tile, delta_detail::tile_has_aggregate, tile_heads); }
+				base = delta_detail::look_back<8>(head_counts, tile, tile);
+			}
+			if (lane == 0) {
+				delta_detail::publish<8>(head_counts + tile, delta_detail::tile_has_inclusive, base + tile_heads);
+				shared_base = base; shared_split = split;
+				if (tile + 1 == num_tiles) { *total_out = base + tile_heads; }
+			}
+		}
+		__syncthreads();
+		const uint64_t base = shared_base, split = shared_split;
+		if (split != no_position && split >= first && split < first + run_tile_per_thread) { mask |= 1u << (unsigned)(split - first); }
+		// exclusive scan of the head counts over the block
+		const unsigned count = __popc(mask);
+		const unsigned inclusive = warp_inclusive_sum(count);
+		if (lane == warp_size - 1) { warp_totals[warp] = inclusive; }
+		__syncthreads();
+		unsigned slot = inclusive - count, tile_heads = 0;
+		#pragma unroll
+		for (unsigned w = 0; w < warps; w++) {
+			const unsigned t = warp_totals[w];
+			if (w < warp) { slot += t; }
+			tile_heads += t;
+		}
+		for (unsigned heads = mask; heads != 0; heads &= heads - 1, slot++) {
+			const unsigned j = __ffs((int) heads) - 1;
+			staged_values[slot] = __ldg(x + first + j);
+			staged_positions[slot] = (uint16_t)(threadIdx.x * run_tile_per_thread + j);
+		}
+		__syncthreads();
+		for (unsigned e = threadIdx.x; e < tile_heads; e += run_tile_threads) {
+			if (base + e < run_capacity) { run_data[base + e] = staged_values[e]; starts[base + e] = (Start)(tile_start + staged_positions[e]); }
+			else { raise(status, status_capacity); }
+		}
+		__syncthreads(); // before the next tile reuses the shared arrays (and the ticket)
 	}
 }
 
