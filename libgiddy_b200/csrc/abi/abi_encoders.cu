@@ -133,6 +133,7 @@ struct run_plan_t {
 	uint64_t num_chunks;       // chunks of 1024 tiles
 	uint64_t* chunk_open;      // num_chunks: the chunks' last natural heads, then their exclusive scan
 	uint64_t* chunk_totals;    // num_chunks + 1: the chunks' run counts, then their exclusive scan; [num_chunks] = the number of runs
+	uint64_t* total;           // where the emission leaves the number of runs for the kernels after it
 };
 
 size_t run_workspace_bytes(uint64_t n, uint64_t run_capacity, run_plan_t& plan)
@@ -151,25 +152,28 @@ void run_workspace_layout(void* memory, uint64_t run_capacity, run_plan_t& plan)
 	plan.starts = reinterpret_cast<uint64_t*>(p); p += (run_capacity + 1) * 8;
 	plan.chunk_open = reinterpret_cast<uint64_t*>(p); p += plan.num_chunks * 8;
 	plan.chunk_totals = reinterpret_cast<uint64_t*>(p);
+	plan.total = plan.placement + plan.num_tiles;
 }
 
 template <unsigned U>
-giddy_status_t run_common(cudaStream_t s, const giddy_launch_config_t* cfg, const run_plan_t& plan, void* run_data, const void* in, uint64_t n,
+giddy_status_t run_common(cudaStream_t s, const giddy_launch_config_t* cfg, run_plan_t& plan, void* run_data, const void* in, uint64_t n,
 	uint64_t max_run_length, uint64_t run_capacity, unsigned* status)
 {
 	const unsigned blocks = cfg->grid_dimensions[0] ? cfg->grid_dimensions[0] : helper_blocks(plan.num_tiles, 1);
 	auto x = static_cast<const uint_t<U>*>(in);
 	// runs limited to at least a tile's length (or not at all) have at most one split point per tile: the mask-based kernels
 	const bool fast = max_run_length == 0 || max_run_length >= enc::run_tile_elements;
-	if (fast && GIDDY_RUN_ENCODERS_SINGLE_PASS) {
-		// ONE pass over the column: a tile's first run index and open run come from its predecessors' descriptors (decoupled
-		// look-back), which live where the two-pass path keeps its summaries and placement: 32 bytes per tile, then the run
-		// count (where the later kernels look for it: placement[num_tiles]) and the ticket counter, all zeroed
-		cudaError_t error = cudaMemsetAsync(plan.summaries, 0, plan.num_tiles * 32 + 16, s);
+	if (GIDDY_RUN_ENCODERS_SINGLE_PASS && (max_run_length == 0 || max_run_length >= enc::run_super_elements)) {
+		// ONE pass over the column: a super-tile's first run index and open run come from its predecessors' descriptors
+		// (decoupled look-back), which live where the two-pass path keeps its summaries: 32 bytes per super-tile, then the run
+		// count and the ticket counter, all zeroed
+		const uint64_t num_super_tiles = (n + enc::run_super_elements - 1) / enc::run_super_elements;
+		cudaError_t error = cudaMemsetAsync(plan.summaries, 0, num_super_tiles * 32 + 16, s);
 		if (error != cudaSuccess) { return fail_cuda(error, "cudaMemsetAsync (run encoder tile descriptors)"); }
-		const unsigned enough = helper_blocks(plan.num_tiles, 1) / 2; // 8 CTAs per multiprocessor
+		const unsigned enough = helper_blocks(num_super_tiles, 1);
 		enc::run_encode_single_pass<U, uint64_t><<<blocks < enough ? blocks : enough, enc::run_tile_threads, 0, s>>>(static_cast<uint_t<U>*>(run_data), plan.starts, x,
 			plan.summaries, n, max_run_length, run_capacity, status);
+		plan.total = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(plan.summaries) + num_super_tiles * 32);
 		return launched("kernel launch (run encoding, one pass)");
 	}
 	if (fast) { enc::run_tile_summaries_fast<U><<<blocks, enc::run_tile_threads, 0, s>>>(plan.summaries, x, n); }
@@ -214,10 +218,10 @@ giddy_status_t rle_launch(void* stream, const giddy_launch_config_t* cfg, void* 
 	giddy_status_t result = run_common<U>(s, cfg, plan, run_data, in, n, max_run_length, run_capacity, status);
 	if (result != GIDDY_SUCCESS) { return result; }
 	enc::run_lengths_from_starts<RL, uint64_t><<<helper_blocks(run_capacity < n ? run_capacity : n, 256), 256, 0, s>>>(
-		static_cast<uint_t<RL>*>(run_lengths), plan.starts, plan.placement + plan.num_tiles, n, run_capacity);
+		static_cast<uint_t<RL>*>(run_lengths), plan.starts, plan.total, n, run_capacity);
 	if ((result = launched("kernel launch (run lengths)")) != GIDDY_SUCCESS) { return result; }
 	enc::run_anchors<RI, RL, uint64_t, true><<<helper_blocks((n + L - 1) / L, 256), 256, 0, s>>>(static_cast<uint_t<RI>*>(anchors), static_cast<uint_t<RL>*>(offsets),
-		num_runs_out, plan.starts, plan.placement + plan.num_tiles, n, L, run_capacity, status);
+		num_runs_out, plan.starts, plan.total, n, L, run_capacity, status);
 	return launched("kernel launch (run anchors)");
 }
 #define RLE_ENTRY(UI, U, RL, RI) { UI, U, RL, RI, reinterpret_cast<const void*>(&enc::run_tile_summaries<U>), &rle_launch<UI, U, RL, RI> }
@@ -250,10 +254,10 @@ giddy_status_t rpe_launch(void* stream, const giddy_launch_config_t* cfg, void* 
 	giddy_status_t result = run_common<U>(s, cfg, plan, run_data, in, n, max_run_length, run_capacity, status);
 	if (result != GIDDY_SUCCESS) { return result; }
 	enc::run_positions_from_starts<PO, uint64_t><<<helper_blocks(run_capacity < n ? run_capacity : n, 256), 256, 0, s>>>(
-		static_cast<uint_t<PO>*>(positions), plan.starts, plan.placement + plan.num_tiles, L, relative, run_capacity, status);
+		static_cast<uint_t<PO>*>(positions), plan.starts, plan.total, L, relative, run_capacity, status);
 	if ((result = launched("kernel launch (run start positions)")) != GIDDY_SUCCESS) { return result; }
 	enc::run_anchors<RI, 1, uint64_t, false><<<helper_blocks((n + L - 1) / L, 256), 256, 0, s>>>(static_cast<uint_t<RI>*>(anchors), nullptr,
-		num_runs_out, plan.starts, plan.placement + plan.num_tiles, n, L, run_capacity, status);
+		num_runs_out, plan.starts, plan.total, n, L, run_capacity, status);
 	return launched("kernel launch (run anchors)");
 }
 #define RPE_ENTRY(UI, U, PO, RI) { UI, U, PO, RI, reinterpret_cast<const void*>(&enc::run_tile_summaries<U>), &rpe_launch<UI, U, PO, RI> }

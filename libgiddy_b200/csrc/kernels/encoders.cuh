@@ -922,7 +922,8 @@ __global__ void __launch_bounds__(run_tile_threads) run_emit_fast(
 //   B  the number of run heads (natural ones + the at most one split point, known once A's look-back is) -- an ordinary
 //      sum look-back gives the index of the tile's first run.
 // Tiles are drawn from a ticket counter, in order: a tile's predecessors are running or done whatever the grid.
-// workspace: descriptors A [num_tiles], descriptors B [num_tiles], the run count (8 bytes), the ticket counter (8 bytes), zeroed.
+// workspace: descriptors A [num_super_tiles], descriptors B [num_super_tiles], the run count (8 bytes), the ticket counter (8
+// bytes), zeroed.
 __device__ __forceinline__ uint64_t look_back_to_nearest(const delta_detail::tile_descriptor_t* descriptors, uint64_t tile)
 {
 	// called by one whole warp for tile >= 1: the value of the nearest predecessor whose descriptor is inclusive, all nearer
@@ -944,6 +945,16 @@ __device__ __forceinline__ uint64_t look_back_to_nearest(const delta_detail::til
 	}
 }
 
+// A look-back covers a SUPER-TILE of run_super_tiles consecutive tiles -- small tiles mean as many descriptors in flight as
+// there are CTAs, and look-backs over a thousand predecessors (measured: slower than the two passes) -- whose run heads are
+// compacted into shared memory tile by tile while the CTA reads it; after the look-backs they leave as one contiguous,
+// coalesced block.  The split point, if there is one, lies before the super-tile's first natural head: entry 0 of the block
+// is kept for it.  (A super-tile with more heads than the shared arrays hold -- runs of fewer than 4-8 elements on
+// average -- is read again, tile by tile, and written straight from registers.)
+constexpr unsigned run_super_tiles = 8;
+constexpr unsigned run_super_elements = run_super_tiles * run_tile_elements; // 32 768: positions within fit 16 bits
+template <unsigned U> struct run_staging { static constexpr unsigned capacity = (U >= 8) ? 4096 : (U == 4 ? 6144 : 8192); };
+
 template <unsigned U, typename Start>
 __global__ void __launch_bounds__(run_tile_threads) run_encode_single_pass(
 	uint_t<U>*        __restrict__  run_data,
@@ -951,21 +962,22 @@ __global__ void __launch_bounds__(run_tile_threads) run_encode_single_pass(
 	const uint_t<U>*  __restrict__  x,
 	void*                           workspace,
 	uint64_t                        length,
-	uint64_t                        max_run_length,   // 0, or at least run_tile_elements
+	uint64_t                        max_run_length,   // 0, or at least run_super_elements
 	uint64_t                        run_capacity,
 	unsigned*                       status)
 {
 	using delta_detail::tile_descriptor_t;
 	constexpr unsigned warps = run_tile_threads / warp_size;
-	__shared__ unsigned   shared_first[warps], shared_last[warps], shared_count[warps];
-	__shared__ unsigned   warp_totals[warps];
+	constexpr unsigned capacity = run_staging<U>::capacity;
+	__shared__ unsigned   shared_first[warps], shared_last[warps];
+	__shared__ unsigned   warp_totals[2][warps];
 	__shared__ uint64_t   shared_ticket, shared_base, shared_split;
-	__shared__ uint_t<U>  staged_values[run_tile_elements];
-	__shared__ uint16_t   staged_positions[run_tile_elements];
-	const uint64_t num_tiles = (length + run_tile_elements - 1) / run_tile_elements;
+	__shared__ uint_t<U>  staged_values[capacity];
+	__shared__ uint16_t   staged_positions[capacity];
+	const uint64_t num_super_tiles = (length + run_super_elements - 1) / run_super_elements;
 	tile_descriptor_t* const last_heads = static_cast<tile_descriptor_t*>(workspace);   // A
-	tile_descriptor_t* const head_counts = last_heads + num_tiles;                       // B
-	uint64_t* const total_out = reinterpret_cast<uint64_t*>(head_counts + num_tiles);
+	tile_descriptor_t* const head_counts = last_heads + num_super_tiles;                 // B
+	uint64_t* const total_out = reinterpret_cast<uint64_t*>(head_counts + num_super_tiles);
 	unsigned long long* const ticket_counter = reinterpret_cast<unsigned long long*>(total_out + 1);
 	const bool vector_loads = is_aligned_to(x, 16);
 	const unsigned lane = lane_index(), warp = warp_index_in_block();
@@ -973,45 +985,68 @@ __global__ void __launch_bounds__(run_tile_threads) run_encode_single_pass(
 		if (threadIdx.x == 0) { shared_ticket = atomicAdd(ticket_counter, 1ull); }
 		__syncthreads();
 		const uint64_t tile = shared_ticket;
-		if (tile >= num_tiles) { return; }
-		const uint64_t tile_start = tile * run_tile_elements;
-		const uint64_t first = tile_start + (uint64_t) threadIdx.x * run_tile_per_thread;
-		uint_t<U> v[run_tile_per_thread];
-		load_16_elements<U>(v, x, first, length, vector_loads);
-		unsigned mask = natural_heads_of_16<U>(v, x, first, length);
-		// the tile's natural heads: how many, the first and the last (tile-relative; one REDUX each)
-		{
-			const unsigned thread_first = threadIdx.x * run_tile_per_thread;
-			const unsigned lowest = __reduce_min_sync(full_mask, mask ? thread_first + (__ffs((int) mask) - 1) : ~0u);
-			const unsigned highest = __reduce_max_sync(full_mask, mask ? thread_first + (32 - __clz((int) mask)) : 0u); // position + 1
-			const unsigned count = __reduce_add_sync(full_mask, (unsigned) __popc(mask));
-			if (lane == 0) { shared_first[warp] = lowest; shared_last[warp] = highest; shared_count[warp] = count; }
+		if (tile >= num_super_tiles) { return; }
+		const uint64_t tile_start = tile * run_super_elements;
+		// 1. the super-tile's natural heads, tile by tile: counted, and compacted into shared memory from entry 1 on
+		unsigned natural = 0;                 // natural heads so far (the same in every thread)
+		unsigned lowest = ~0u, highest = 0u;  // this thread's first head, and last head + 1, relative to the super-tile
+		#pragma unroll 1
+		for (unsigned k = 0; k < run_super_tiles; k++) {
+			const uint64_t first = tile_start + (uint64_t) k * run_tile_elements + (uint64_t) threadIdx.x * run_tile_per_thread;
+			if (first - (uint64_t) threadIdx.x * run_tile_per_thread >= length) { break; }
+			uint_t<U> v[run_tile_per_thread];
+			load_16_elements<U>(v, x, first, length, vector_loads);
+			const unsigned mask = natural_heads_of_16<U>(v, x, first, length);
+			const unsigned relative = k * run_tile_elements + threadIdx.x * run_tile_per_thread;
+			if (mask) { if (lowest == ~0u) { lowest = relative + (__ffs((int) mask) - 1); } highest = relative + (32 - __clz((int) mask)); }
+			const unsigned count = __popc(mask);
+			const unsigned inclusive = warp_inclusive_sum(count);
+			if (lane == warp_size - 1) { warp_totals[k & 1u][warp] = inclusive; }
+			__syncthreads();
+			unsigned slot = 1 + natural + inclusive - count, tile_heads = 0;
+			#pragma unroll
+			for (unsigned w = 0; w < warps; w++) {
+				const unsigned t = warp_totals[k & 1u][w];
+				if (w < warp) { slot += t; }
+				tile_heads += t;
+			}
+			natural += tile_heads;
+			if (1 + natural <= capacity) {
+				for (unsigned heads = mask; heads != 0; heads &= heads - 1, slot++) {
+					const unsigned j = __ffs((int) heads) - 1;
+					staged_values[slot] = __ldg(x + first + j);
+					staged_positions[slot] = (uint16_t)(relative + j);
+				}
+			}
 		}
+		lowest = __reduce_min_sync(full_mask, lowest);
+		highest = __reduce_max_sync(full_mask, highest);
+		if (lane == 0) { shared_first[warp] = lowest; shared_last[warp] = highest; }
 		__syncthreads();
+		// 2. warp 0: the run open at the super-tile's start (hence its split point) and the index of its first run
 		if (warp == 0) {
 			const bool has = lane < warps;
-			const unsigned lowest = __reduce_min_sync(full_mask, has ? shared_first[lane] : ~0u);
-			const unsigned highest = __reduce_max_sync(full_mask, has ? shared_last[lane] : 0u);
-			const unsigned natural = __reduce_add_sync(full_mask, has ? shared_count[lane] : 0u);
+			lowest = __reduce_min_sync(full_mask, has ? shared_first[lane] : ~0u);
+			highest = __reduce_max_sync(full_mask, has ? shared_last[lane] : 0u);
 			const bool has_head = highest != 0;
-			// A: a tile with a head knows its last head at once
+			// A: a super-tile with a head knows its last head at once
 			if (lane == 0) {
 				if (has_head) { delta_detail::publish<8>(last_heads + tile, delta_detail::tile_has_inclusive, tile_start + highest - 1); }
 				else { delta_detail::publish<8>(last_heads + tile, delta_detail::tile_has_aggregate, 0ull); }
 			}
 			uint64_t split = no_position;
 			if (tile != 0 && (max_run_length != 0 || !has_head)) {
-				const uint64_t origin = look_back_to_nearest(last_heads, tile); // where the run open at the tile's start began
+				const uint64_t origin = look_back_to_nearest(last_heads, tile); // where the run open at the super-tile's start began
 				if (!has_head && lane == 0) { delta_detail::publish<8>(last_heads + tile, delta_detail::tile_has_inclusive, origin); }
 				if (max_run_length != 0) {
-					// the one split point this tile can hold: in the part of the open run which precedes the tile's first natural head
+					// the one split point a super-tile can hold: in the part of the open run which precedes its first natural head
 					const uint64_t distance = tile_start - origin;
 					const uint64_t candidate = origin + (distance <= max_run_length ? max_run_length : (distance + max_run_length - 1) / max_run_length * max_run_length);
-					const uint64_t prefix_end = has_head ? tile_start + lowest : minimum<uint64_t>(tile_start + run_tile_elements, length);
+					const uint64_t prefix_end = has_head ? tile_start + lowest : minimum<uint64_t>(tile_start + run_super_elements, length);
 					if (candidate < prefix_end) { split = candidate; }
 				}
 			}
-			// B: the tile's head count, then the index of its first run
+			// B: the super-tile's head count, then the index of its first run
 			const uint64_t tile_heads = (uint64_t) natural + (split != no_position ? 1u : 0u);
 			uint64_t base = 0;
 			if (tile != 0) {
@@ -1021,35 +1056,56 @@ __global__ void __launch_bounds__(run_tile_threads) run_encode_single_pass(
 			if (lane == 0) {
 				delta_detail::publish<8>(head_counts + tile, delta_detail::tile_has_inclusive, base + tile_heads);
 				shared_base = base; shared_split = split;
-				if (tile + 1 == num_tiles) { *total_out = base + tile_heads; }
+				if (tile + 1 == num_super_tiles) { *total_out = base + tile_heads; }
+				if (split != no_position) { staged_values[0] = __ldg(x + split); staged_positions[0] = (uint16_t)(split - tile_start); }
 			}
 		}
 		__syncthreads();
-		const uint64_t base = shared_base, split = shared_split;
-		if (split != no_position && split >= first && split < first + run_tile_per_thread) { mask |= 1u << (unsigned)(split - first); }
-		// exclusive scan of the head counts over the block
-		const unsigned count = __popc(mask);
-		const unsigned inclusive = warp_inclusive_sum(count);
-		if (lane == warp_size - 1) { warp_totals[warp] = inclusive; }
-		__syncthreads();
-		unsigned slot = inclusive - count, tile_heads = 0;
-		#pragma unroll
-		for (unsigned w = 0; w < warps; w++) {
-			const unsigned t = warp_totals[w];
-			if (w < warp) { slot += t; }
-			tile_heads += t;
+		// 3. the block of (value, start) pairs
+		const uint64_t split = shared_split;
+		const unsigned skipped = (split != no_position) ? 0u : 1u;          // entry 0 is the split point's
+		const uint64_t base = shared_base - skipped;                          // run index of entry 0
+		const unsigned past_last = 1 + natural;
+		if (past_last <= capacity) {
+			for (unsigned e = skipped + threadIdx.x; e < past_last; e += run_tile_threads) {
+				if (base + e < run_capacity) { run_data[base + e] = staged_values[e]; starts[base + e] = (Start)(tile_start + staged_positions[e]); }
+				else { raise(status, status_capacity); }
+			}
 		}
-		for (unsigned heads = mask; heads != 0; heads &= heads - 1, slot++) {
-			const unsigned j = __ffs((int) heads) - 1;
-			staged_values[slot] = __ldg(x + first + j);
-			staged_positions[slot] = (uint16_t)(threadIdx.x * run_tile_per_thread + j);
+		else { // more heads than the shared arrays hold: the tiles again, written from registers
+			uint64_t next = shared_base; // run index of the next head
+			if (split != no_position) {
+				if (threadIdx.x == 0) { if (next < run_capacity) { run_data[next] = __ldg(x + split); starts[next] = (Start) split; } else { raise(status, status_capacity); } }
+				next++;
+			}
+			#pragma unroll 1
+			for (unsigned k = 0; k < run_super_tiles; k++) {
+				const uint64_t first = tile_start + (uint64_t) k * run_tile_elements + (uint64_t) threadIdx.x * run_tile_per_thread;
+				if (first - (uint64_t) threadIdx.x * run_tile_per_thread >= length) { break; }
+				uint_t<U> v[run_tile_per_thread];
+				load_16_elements<U>(v, x, first, length, vector_loads);
+				const unsigned mask = natural_heads_of_16<U>(v, x, first, length);
+				const unsigned count = __popc(mask);
+				const unsigned inclusive = warp_inclusive_sum(count);
+				__syncthreads(); // (the totals of the tile before have been read)
+				if (lane == warp_size - 1) { warp_totals[0][warp] = inclusive; }
+				__syncthreads();
+				uint64_t at = next + inclusive - count;
+				unsigned tile_heads = 0;
+				#pragma unroll
+				for (unsigned w = 0; w < warps; w++) {
+					const unsigned t = warp_totals[0][w];
+					if (w < warp) { at += t; }
+					tile_heads += t;
+				}
+				for (unsigned heads = mask; heads != 0; heads &= heads - 1, at++) {
+					const unsigned j = __ffs((int) heads) - 1;
+					if (at < run_capacity) { run_data[at] = __ldg(x + first + j); starts[at] = (Start)(first + j); } else { raise(status, status_capacity); }
+				}
+				next += tile_heads;
+			}
 		}
-		__syncthreads();
-		for (unsigned e = threadIdx.x; e < tile_heads; e += run_tile_threads) {
-			if (base + e < run_capacity) { run_data[base + e] = staged_values[e]; starts[base + e] = (Start)(tile_start + staged_positions[e]); }
-			else { raise(status, status_capacity); }
-		}
-		__syncthreads(); // before the next tile reuses the shared arrays (and the ticket)
+		__syncthreads(); // before the next super-tile reuses the shared arrays (and the ticket)
 	}
 }
 

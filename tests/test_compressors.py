@@ -175,6 +175,15 @@ def test_run_length_encoding_shapes(library, n, L, mean_run, max_run_length):
     _check_rle(library, 4, 4, 2, n, L, mean_run, max_run_length)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("RL,max_run_length", [(2, 0), (4, 40000), (4, 32768), (2, 50000), (4, 0)])
+@pytest.mark.parametrize("n,mean_run", [(500000 + 11, 120000), (1 << 20, 30000), (300000, 300000)])
+def test_run_length_encoding_runs_longer_than_a_super_tile(library, RL, max_run_length, n, mean_run):
+    """The one-pass encoder: super-tiles of 32768 elements without a run head, split points of runs which began several
+    super-tiles earlier (at the length type's limit, or at a limit of the caller's)."""
+    _check_rle(library, 4, 4, RL, n, 1024, mean_run, max_run_length)
+
+
 def _check_rle(library, I, U, RL, n, L, mean_run, max_run_length=0):
     import torch
     column = cases._random_runs_column(cases.rng(35, n, L, U, RL), n, U, mean_run)
