@@ -72,6 +72,15 @@ launches)
 	timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/${TAG}_launches.csv \
 		python bench.py --steps 5 --warmup 3 --skip-cpu --skip-verify --configs-repeats 2 > $OUT/${TAG}_launches_bench.log 2>&1
 	wc -l $OUT/${TAG}_launches.csv ;;
+sanitize)
+	# compute-sanitizer over the product-vs-oracle tests, the compressors, the utility kernels and smoke (no reference kernels: their Delta races)
+	for tool in memcheck racecheck synccheck; do
+		timeout 2400 compute-sanitizer --tool $tool --error-exitcode 7 python -m pytest tests/test_gpu_parity.py tests/test_compressors.py tests/test_utility_kernels.py tests/test_host_resident_scan.py \
+			-m gpu -q -x -k "not matches_reference_kernels" > $OUT/${TAG}_sanitize_$tool.txt 2>&1
+		echo "$tool: rc=$? $(grep -E 'passed|failed' $OUT/${TAG}_sanitize_$tool.txt | tail -1) | $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $OUT/${TAG}_sanitize_$tool.txt | tail -1)"
+	done
+	timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_sanitize_smoke.txt 2>&1
+	echo "smoke memcheck: rc=$? $(grep -E 'ERROR SUMMARY' $OUT/${TAG}_sanitize_smoke.txt | tail -1)" ;;
 *) echo "unknown step $what" ;;
 esac
 done
