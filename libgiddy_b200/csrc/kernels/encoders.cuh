@@ -7,9 +7,10 @@
 // per-segment model coefficients (FOR), the value preceding each segment (Delta), the run index and intra-run offset of
 // each segment's first element (RLE / RPE), the byte offset of each segment's first element (DZB-variable).
 //
-// Position-aligned encoders (Delta, DZB-fixed, Dictionary lookup, FOR) are single streaming kernels.  The encoders with
-// data-dependent output positions (RLE, RPE, DZB-variable) are two passes over the column around an exclusive scan of
-// per-tile (per-segment) counts: pass 1 counts, the scan places, pass 2 writes.  Every encoder raises bits of an
+// Position-aligned encoders (Delta, DZB-fixed, Dictionary lookup, FOR) are single streaming kernels.  Of the encoders with
+// data-dependent output positions, RLE and RPE take ONE pass with decoupled look-back over super-tiles (run_encode_single_pass)
+// unless runs are to be cut shorter than a super-tile, and then -- like DZB-variable always -- two passes over the column
+// around an exclusive scan of per-tile (per-segment) counts: pass 1 counts, the scan places, pass 2 writes.  Every encoder raises bits of an
 // optional status word instead of writing garbage when the data does not fit the format (a delta too wide for the
 // compressed type, a value missing from the dictionary, more runs than the caller's arrays hold).
 #pragma once
