@@ -30,7 +30,7 @@ HEADLINE = [
     "incidence_bitmaps_decompress<4, 4, 2, true>", "scatter<4, 8, 4>", "compressed_indices_scatter<4, 4, 4, 4>",
     "patched_dictionary_decompress<4, 8, 1>", "patched_frame_of_reference_decompress<4, 4, 2, 1, 4>", "expand_compressed_indices<4, 4, 4>", "patched_detail::patch_tile_ranges<4>",
     "patched_detail::expand_and_index_compressed_indices<4, 4, 4>",
-    "encoders::run_tile_summaries_fast<4>", "encoders::run_emit_fast<4, unsigned long>", "encoders::delta_compress<4, 8, 4>",
+    "encoders::run_encode_single_pass<4, unsigned long>", "encoders::run_tile_summaries_fast<4>", "encoders::run_emit_fast<4, unsigned long>", "encoders::delta_compress<4, 8, 4>",
     "encoders::frame_of_reference_compress<4, 4, 2, 0>", "encoders::dictionary_compress<4, 8, 1>", "encoders::variable_width_emit<4, 4>",
 ]
 
