@@ -36,3 +36,15 @@ def test_sharded_scan_over_all_visible_gpus(library):
     result = subprocess.run([binary, "22"], capture_output=True, text=True, timeout=600)
     assert result.returncode == 0, result.stdout + result.stderr
     assert result.stdout.count("SUCCESS") == 3, result.stdout
+
+
+@pytest.mark.gpu
+def test_compress_and_decompress_through_the_factory(library):
+    """examples/compress_roundtrip.cpp: the compressors' factory keys used from C++ in the reference's mode (iii) idiom -- RLE
+    there and back, and Delta + DZB-variable compressed by two kernels and decompressed by the one fused decoder."""
+    binary = os.path.join(ROOT, "examples", "bin", "compress_roundtrip")
+    if not os.path.exists(binary):
+        subprocess.run(["make", "-C", ROOT, "examples"], check=True, capture_output=True)
+    result = subprocess.run([binary, "22"], capture_output=True, text=True, timeout=600)
+    assert result.returncode == 0, result.stdout + result.stderr
+    assert result.stdout.count("SUCCESS") == 2, result.stdout
