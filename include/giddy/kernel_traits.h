@@ -78,6 +78,9 @@
 #ifndef GIDDY_PATCHED_INDEX_BLOCK_THREADS
 #define GIDDY_PATCHED_INDEX_BLOCK_THREADS 64       /* expand_and_index_compressed_indices: a CTA per anchoring period */
 #endif
+#ifndef GIDDY_PATCHED_EARLY_TILES
+#define GIDDY_PATCHED_EARLY_TILES 2                /* tiles a warp decodes ahead of the tile index (programmatic dependent launch) */
+#endif
 #ifndef GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR
 #define GIDDY_PATCHED_BLOCKS_PER_MULTIPROCESSOR 4
 #endif

@@ -59,6 +59,30 @@ inline giddy_status_t launch(Kernel kernel, void* stream, const giddy_launch_con
 	return GIDDY_SUCCESS;
 }
 
+// The same, as a programmatic dependent of the kernel before it on the stream (kernels/common.cuh): it may be scheduled
+// while that kernel drains, and waits for it on the device where it first needs its results.  An ordinary launch where the
+// attribute is refused.
+template <typename... Params, typename... Args>
+inline giddy_status_t launch_as_dependent(void (*kernel)(Params...), void* stream, const giddy_launch_config_t* config, Args... args)
+{
+	cudaError_t error = ensure_dynamic_shared_memory(reinterpret_cast<const void*>(kernel), config->dynamic_shared_memory_size);
+	if (error != cudaSuccess) { return fail_cuda(error, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); }
+	cudaLaunchConfig_t launch_config = { };
+	launch_config.gridDim = to_dim3(config->grid_dimensions);
+	launch_config.blockDim = to_dim3(config->block_dimensions);
+	launch_config.dynamicSmemBytes = config->dynamic_shared_memory_size;
+	launch_config.stream = static_cast<cudaStream_t>(stream);
+	cudaLaunchAttribute attribute = { };
+	attribute.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attribute.val.programmaticStreamSerializationAllowed = 1;
+	launch_config.attrs = &attribute;
+	launch_config.numAttrs = 1;
+	error = cudaLaunchKernelEx(&launch_config, kernel, static_cast<Params>(args)...);
+	if (error == cudaSuccess) { return GIDDY_SUCCESS; }
+	cudaGetLastError();
+	return launch(kernel, stream, config, args...);
+}
+
 } // namespace abi
 } // namespace giddy
 

@@ -60,7 +60,7 @@ giddy_status_t dict_launch(void* stream, const giddy_launch_config_t* cfg, void*
 	if (error != cudaSuccess) { cudaFreeAsync(offsets, s); return fail_cuda(error, "cudaMemsetAsync (patch tile index)"); }
 	giddy_status_t status = build_tile_index<I>(s, offsets, patch_indices, num_patches, log2_tile, num_tiles, n);
 	if (status == GIDDY_SUCCESS) {
-		status = launch(kernels::patched_dictionary_decompress<I, U, DI>, stream, cfg,
+		status = launch_as_dependent(kernels::patched_dictionary_decompress<I, U, DI>, stream, cfg,
 			static_cast<uint_t<U>*>(out), static_cast<const uint_t<DI>*>(in), static_cast<const uint_t<U>*>(dict),
 			(size_type<I>) n, (size_type<DI>) num_entries, cache,
 			static_cast<const uint_t<U>*>(patch_data), static_cast<const uint_t<I>*>(patch_indices),
@@ -139,7 +139,7 @@ giddy_status_t for_launch(void* stream, const giddy_launch_config_t* cfg, void* 
 	}
 	if (status == GIDDY_SUCCESS && !index_built) { status = build_tile_index<I>(s, workspace, positions, data_length, log2_tile, num_tiles, n); }
 	if (status == GIDDY_SUCCESS) {
-		status = launch(kernels::patched_frame_of_reference_decompress<I, U, C, M, MI>, stream, cfg,
+		status = launch_as_dependent(kernels::patched_frame_of_reference_decompress<I, U, C, M, MI>, stream, cfg,
 			static_cast<uint_t<U>*>(out), static_cast<const int_t<C>*>(in), static_cast<const int32_t*>(coeffs),
 			(size_type<I>) n, (size_type<I>) L,
 			static_cast<const uint_t<U>*>(data), static_cast<const uint_t<I>*>(positions), static_cast<const kernels::patched_detail::patch_range_t<I>*>(workspace), log2_tile);

@@ -218,6 +218,14 @@ __device__ __forceinline__ void tma_bulk_load(void* shared_destination, const vo
 		:: "r"(shared_address(shared_destination)), "l"(global_source), "r"(bytes), "r"(shared_address(barrier)) : "memory");
 }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while the kernel before it on the
+// stream is still running -- as soon as all of that kernel's CTAs have called launch_dependent_grids() (or exited) -- and
+// must call wait_for_prerequisite_grids() before it touches anything that kernel writes: the call returns once the earlier
+// kernel has completed and its writes are visible.  Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void launch_dependent_grids() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void wait_for_prerequisite_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t dynamic_shared_memory_size()
 {
 	uint32_t r;

@@ -59,6 +59,7 @@ constexpr unsigned blocks_per_multiprocessor(unsigned index_size, unsigned eleme
 // Same arithmetic as the stand-alone kernels in elementwise.cuh.
 
 constexpr unsigned piece_bytes = 32;
+constexpr unsigned early_tiles = GIDDY_PATCHED_EARLY_TILES; // tiles a warp decodes before it needs the tile index
 
 __device__ __forceinline__ void store_piece(void* p, const byte_pack<piece_bytes>& v)
 {
@@ -150,6 +151,7 @@ __global__ void patch_tile_ranges(
 	unsigned                                 log2_tile_elements,
 	uint64_t                                 length)
 {
+	launch_dependent_grids(); // (the decoder may be scheduled as this kernel drains; it waits for the index on the device)
 	// a thread takes 4 consecutive patches (one 16-byte load of 32-bit positions) and their two neighbours
 	constexpr unsigned per_thread = 4;
 	const bool wide = IndexSize == 4 && is_aligned_to(positions, 16);
@@ -204,6 +206,7 @@ __global__ void expand_and_index_compressed_indices(
 	unsigned                                      log2_tile_elements,
 	uint64_t                                      length)
 {
+	launch_dependent_grids(); // (the decoder may be scheduled as this kernel drains; it waits for the index on the device)
 	using position_t = uint_t<OutputIndexSize>;
 	constexpr unsigned batch = 8; // patches per lane with their offset loads in flight at once
 	__shared__ uint32_t   ends[warp_size];           // inclusive scan of the staged runs' lengths
@@ -328,6 +331,7 @@ __device__ __forceinline__ void decode_and_patch(
 	if (first_tile >= num_tiles) { return; }
 
 	if (!vectorizable) { // misaligned buffers: element by element, patches stored after their elements
+		wait_for_prerequisite_grids(); // (the tile index is another kernel's: see below)
 		#pragma unroll 1
 		for (uint64_t tile = first_tile; tile < num_tiles; tile += tile_stride) {
 			const uint64_t tile_start = tile << log2_tile_elements;
@@ -362,7 +366,51 @@ __device__ __forceinline__ void decode_and_patch(
 		return p;
 	};
 
+	// The kernel is launched as a programmatic dependent of the kernel which builds the tile index (abi/abi_patched.cu): a warp
+	// decodes and stores its first tiles without looking at the index -- work which overlaps that kernel's tail instead of
+	// waiting behind it --, then waits for the index, applies those tiles' patches, and carries on with the pipelined loop.
 	index_t tile = (index_t) first_tile;
+	unsigned early = 0;
+	#pragma unroll 1
+	for (; early < early_tiles && (uint64_t) tile < num_tiles; early++, tile += (index_t) tile_stride) {
+		const index_t tile_start = tile << log2_tile_elements;
+		const index_t first_piece = tile * pieces_per_tile;
+		const bool whole = tile + 1 != num_tiles || (uint64_t) tile_start + elements_per_tile == length;
+		const index_t tile_end = whole ? tile_start + elements_per_tile : length;
+		const unsigned num_pieces = whole ? pieces_per_tile : (unsigned)(tile_end / E - first_piece);
+		byte_pack<Decoder::in_bytes> in[unroll];
+		#pragma unroll
+		for (unsigned k = 0; k < unroll; k++) {
+			const unsigned v = k * warp_size + lane;
+			if (v < num_pieces) { in[k] = decoder.load(first_piece + v); }
+		}
+		#pragma unroll
+		for (unsigned k = 0; k < unroll; k++) {
+			const unsigned v = k * warp_size + lane;
+			if (v < num_pieces) { store_piece(decompressed + (uint64_t)(first_piece + v) * E, decoder.decode(in[k], first_piece + v)); }
+		}
+		if (!whole) {
+			const uint64_t i = (uint64_t)(first_piece + num_pieces) * E + lane;
+			if (i < tile_end) { decompressed[i] = decoder.decode_one(i); }
+		}
+	}
+	wait_for_prerequisite_grids();
+	__syncwarp();
+	{
+		index_t patched = (index_t) first_tile;
+		#pragma unroll 1
+		for (unsigned e = 0; e < early; e++, patched += (index_t) tile_stride) {
+			const patch_range_t<IndexSize> early_range = tile_ranges[patched];
+			const index_t tile_start = patched << log2_tile_elements;
+			const index_t tile_length = (index_t) minimum<uint64_t>(elements_per_tile, (uint64_t) length - tile_start);
+			if (early_range.past_last <= early_range.first) { continue; } // (an empty range is all ones: no arithmetic on it)
+			for (uint64_t q = (uint64_t) early_range.first + lane; q < early_range.past_last; q += warp_size) {
+				const index_t position = __ldg(patch_positions + q);
+				if ((index_t)(position - tile_start) < tile_length) { decompressed[position] = __ldg(patch_values + q); }
+			}
+		}
+	}
+	if ((uint64_t) tile >= num_tiles) { return; }
 	patch_range_t<IndexSize> range = tile_ranges[tile];
 	bool has_next = (uint64_t) tile + tile_stride < num_tiles;
 	patch_range_t<IndexSize> range_next = has_next ? tile_ranges[tile + (index_t) tile_stride] : no_patches;
