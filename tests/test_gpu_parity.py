@@ -58,3 +58,28 @@ def test_matches_reference_kernels(case, library, reference_library):
         # and can, rarely, decode wrongly; give it a second run before calling the two libraries different
         theirs = cases.run_case_on_gpu(case, reference_library)
     assert (ours == theirs).all(), _mismatch_report(case, theirs)
+
+
+BACK_TO_BACK = [c for c in ALL_CASES if c.name.startswith(("patched-dict-I4-U8-DI1-D256-n1048576", "patched-for-linear-I4-U4-C2-n1048576"))]
+
+
+@pytest.mark.parametrize("case", BACK_TO_BACK, ids=lambda c: c.name)
+def test_fused_patched_decoders_back_to_back(case, library):
+    """The patched decoders are programmatic dependent launches of the kernel which builds their tile index (they may start while
+    it drains, and wait for it on the device): 48 calls enqueued without a synchronisation in between, on two streams, every
+    output checked."""
+    import torch
+    device = torch.device("cuda")
+    tensors = {k: torch.from_numpy(cases._as_torch_compatible(v)).to(device) for k, v in case.inputs.items()}
+    itemsize = case.expected.dtype.itemsize
+    outputs = [torch.full(((case.output_elements + 64) * itemsize,), 0x5A, dtype=torch.uint8, device=device).view(cases._torch_int(itemsize)) for _ in range(48)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for k, out in enumerate(outputs):
+        with torch.cuda.stream(streams[k % 2]):
+            case.launch(out, tensors, library, None)
+    torch.cuda.synchronize()
+    for k, out in enumerate(outputs):
+        got = out.cpu().numpy().view(case.expected.dtype)
+        assert (got[case.output_elements:].view(np.uint8) == 0x5A).all(), "%s, call %d: wrote past the end of the output" % (case.name, k)
+        assert (got[:case.output_elements] == case.expected).all(), "call %d: %s" % (k, _mismatch_report(case, got[:case.output_elements]))
