@@ -108,21 +108,31 @@ giddy_status_t for_launch(void* stream, const giddy_launch_config_t* cfg, void* 
 	// data_length patches leave the rest of the list never applied, as the reference's kernel would).  The fused kernel fills
 	// the uncovered positions itself; the generic path needs the whole list filled beforehand.
 	const bool fused_index = data_length != 0 && anchoring_period * I <= 32 * 1024;
-	error = cudaMemsetAsync(workspace, 0xff, fused_index ? offsets_bytes : offsets_bytes + data_length * I, s);
-	if (error != cudaSuccess) { cudaFreeAsync(workspace, s); return fail_cuda(error, "cudaMemsetAsync (patch positions and tile index)"); }
+	if (fused_index) { // (a kernel, so that the position decode can run as its programmatic dependent)
+		const uint64_t vectors = offsets_bytes / 16;
+		kernels::patched_detail::fill_tile_index<><<<(unsigned) ((vectors + 255) / 256 < 1184 ? (vectors + 255) / 256 : 1184), 256, 0, s>>>(static_cast<uint4*>(workspace), vectors);
+		error = cudaGetLastError();
+	}
+	else { error = cudaMemsetAsync(workspace, 0xff, offsets_bytes + data_length * I, s); }
+	if (error != cudaSuccess) { cudaFreeAsync(workspace, s); return fail_cuda(error, "filling the patch positions and tile index"); }
 	bool index_built = false;
 	if (data_length != 0) {
 		const uint64_t periods = (data_length + anchoring_period - 1) / anchoring_period;
 		// periods whose decoded positions fit 32 KiB keep them in shared memory and build the tile index in the same kernel
 		// (one launch and one pass over the positions less); longer ones leave it to patch_tile_ranges
 		if (fused_index) {
-			kernels::patched_detail::expand_and_index_compressed_indices<I, II, II><<<(unsigned) (periods < 0x7fffffffull ? periods : 0x7fffffffull), GIDDY_PATCHED_INDEX_BLOCK_THREADS,
-				(unsigned)(anchoring_period * I), s>>>(
+			giddy_launch_config_t index_config = { };
+			index_config.grid_dimensions[0] = (unsigned) (periods < 0x7fffffffull ? periods : 0x7fffffffull);
+			index_config.grid_dimensions[1] = index_config.grid_dimensions[2] = 1;
+			index_config.block_dimensions[0] = GIDDY_PATCHED_INDEX_BLOCK_THREADS;
+			index_config.block_dimensions[1] = index_config.block_dimensions[2] = 1;
+			index_config.dynamic_shared_memory_size = (unsigned)(anchoring_period * I);
+			status = launch_as_dependent(kernels::patched_detail::expand_and_index_compressed_indices<I, II, II>, stream, &index_config,
 				static_cast<uint_t<I>*>(positions), static_cast<kernels::patched_detail::patch_range_t<I>*>(workspace),
 				static_cast<const uint_t<II>*>(run_lengths), static_cast<const unsigned char*>(offset_sizes),
 				static_cast<const uint_t<I>*>(baselines), static_cast<const uint_t<II>*>(offsets_start),
 				static_cast<const unsigned char*>(offset_bytes), static_cast<const uint_t<II>*>(anchors),
-				(unsigned) anchoring_period, num_runs, data_length, log2_tile, n);
+				(unsigned) anchoring_period, (uint64_t) num_runs, (uint64_t) data_length, log2_tile, (uint64_t) n);
 		}
 		else {
 			const unsigned warps_per_block = GIDDY_CI_SCATTER_WARPS_PER_BLOCK;

@@ -182,6 +182,17 @@ __global__ void patch_tile_ranges(
 	}
 }
 
+// Every tile's range set to "empty" (all ones), by a kernel rather than a memset node so that the kernel after it can be its
+// programmatic dependent: the positions are decoded while this runs.
+template <unsigned Unused = 0>
+__global__ void fill_tile_index(uint4* __restrict__ index, uint64_t num_vectors)
+{
+	launch_dependent_grids();
+	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < num_vectors; i += (uint64_t) gridDim.x * blockDim.x) {
+		index[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+	}
+}
+
 // The run-compressed positions of a compressed-indices patch list (reference compressed_indices_scatter.cuh:133-231) as a
 // plain list -- positions[k] is where patch value k goes -- AND the tile index of those positions, in one kernel, for lists
 // whose anchoring period is short enough for a period's positions to sit in shared memory (the launcher checks).  A BLOCK
@@ -290,8 +301,10 @@ __global__ void expand_and_index_compressed_indices(
 		// column: never applied, as the reference's kernel would skip them)
 		for (unsigned k = done + threadIdx.x; k < period_patches; k += blockDim.x) { positions[period_first + k] = ~(position_t) 0; }
 		// the tile index for this period's patches (see patch_tile_ranges): patch k opens its tile's range if its predecessor lies
-		// in an earlier tile and closes it if its successor lies in a later one
+		// in an earlier tile and closes it if its successor lies in a later one.  (The index was filled with "empty" by the kernel
+		// before this one, whose programmatic dependent this kernel is: nothing of it has been touched so far.)
 		__syncthreads();
+		wait_for_prerequisite_grids();
 		for (unsigned k = threadIdx.x; k < done; k += blockDim.x) {
 			const position_t position = period_positions[k];
 			if ((uint64_t) position >= length) { continue; }
